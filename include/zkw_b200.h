@@ -1,0 +1,177 @@
+/*
+ * zkw_b200.h — C ABI of the B200-native Halo2 prover hot path (BN254 G1 MSM, BN254 Fr NTT,
+ * coset quotient evaluation) for zkwebauthn/webauthn-halo2's P-256 ECDSA circuit.
+ *
+ * This is the drop-in boundary: the entry points below are what a patched
+ * `halo2_proofs` (reached from the reference at
+ * halo2-circuits/src/ecc/ecdsa_p256.rs:366-373, :416-423, :555-562 [create_proof] and
+ * :259-260 [keygen_vk / keygen_pk]) binds over Rust FFI in place of
+ *
+ *   halo2_proofs::arithmetic::best_multiexp        -> zkw_msm_bn254_g1
+ *   halo2_proofs::arithmetic::best_fft             -> zkw_ntt_bn254_fr
+ *   poly::EvaluationDomain::lagrange_to_coeff      -> zkw_lagrange_to_coeff
+ *   poly::EvaluationDomain::coeff_to_extended      -> zkw_coeff_to_extended
+ *   poly::EvaluationDomain::extended_to_coeff      -> zkw_extended_to_coeff
+ *   plonk::evaluation::Evaluator::evaluate_h
+ *     + EvaluationDomain::divide_by_vanishing_poly -> zkw_quotient_ecdsa
+ *
+ * (those crates are un-vendored dependencies of the reference, Cargo.toml:12-15; see
+ * INTEGRATION.md for the Rust `extern "C"` block and the three patched call sites).
+ *
+ * Conventions
+ *   - Plain C: pointers + sizes, no C++/torch types.  Every function returns ZKW_OK (0) or a
+ *     negative zkw_status; nothing aborts.  zkw_strerror() names a status.
+ *   - Field elements are halo2curves' in-memory form: [u64;4] little-endian limbs in
+ *     Montgomery form (R = 2^256).  G1Affine = {x: Fq, y: Fq}, 64 contiguous bytes, identity
+ *     encoded (0,0).  G1 (projective output) = {x,y,z} Jacobian, 96 bytes, identity z = 0.
+ *   - Pointer arguments named `*_host`/unsuffixed are HOST memory; `_dev` entry points take
+ *     DEVICE pointers valid on the context's device and enqueue on the context's stream
+ *     without synchronising (call zkw_ctx_sync).
+ *   - A zkw_ctx is bound to one CUDA device; use one ctx per GPU (one process per GPU in the
+ *     multi-GPU layout).  Calls on one ctx must be serialised by the caller.
+ *   - There is NO CPU fallback: without a usable CUDA device every call returns
+ *     ZKW_ERR_NO_DEVICE.
+ */
+#ifndef ZKW_B200_H
+#define ZKW_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct zkw_ctx zkw_ctx;
+
+typedef enum {
+    ZKW_OK = 0,
+    ZKW_ERR_NO_DEVICE = -1,   /* no CUDA device / driver: the product path has no CPU fallback */
+    ZKW_ERR_CUDA = -2,        /* a CUDA runtime call failed; zkw_last_cuda_error() has the text */
+    ZKW_ERR_INVALID = -3,     /* bad argument (NULL, size not a power of two, k out of range …) */
+    ZKW_ERR_OOM = -4,         /* device allocation failed */
+    ZKW_ERR_STATE = -5,       /* e.g. MSM against SRS bases before zkw_srs_load */
+    ZKW_ERR_UNSUPPORTED = -6  /* circuit shape outside what the quotient kernel was built for */
+} zkw_status;
+
+/* ---- context ------------------------------------------------------------------------- */
+int zkw_ctx_create(int device, zkw_ctx** out);
+void zkw_ctx_destroy(zkw_ctx* ctx);
+int zkw_ctx_sync(zkw_ctx* ctx);
+/* The CUDA stream (cudaStream_t as void*) every `_dev` call of this ctx is enqueued on. */
+void* zkw_ctx_stream(zkw_ctx* ctx);
+const char* zkw_strerror(int status);
+const char* zkw_last_cuda_error(zkw_ctx* ctx);
+/* Number of kernel launches this ctx has issued since creation (bench.py's gpu_launches). */
+uint64_t zkw_ctx_launch_count(zkw_ctx* ctx);
+
+/* ---- SRS residency: replaces ParamsKZG{g, g_lagrange} living in host Vec<G1Affine> ------ */
+/* Copies n affine points of each basis to the device once; later MSMs name them by id. */
+int zkw_srs_load(zkw_ctx* ctx, const uint64_t* g /* n*8 */, const uint64_t* g_lagrange /* n*8 or NULL */, size_t n);
+
+enum { ZKW_BASES_G = 0, ZKW_BASES_G_LAGRANGE = 1, ZKW_BASES_CALLER = 2 };
+
+/* ---- MSM: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> C::Curve -------------- */
+/* scalars: n*4 u64, Montgomery form as stored by halo2curves (the kernel de-Montgomerises,
+ * the analogue of upstream's `to_repr()`).  bases: n*8 u64 when which_bases == ZKW_BASES_CALLER,
+ * else ignored.  out_xyz: Jacobian (X,Y,Z) Montgomery, identity => Z = 0. */
+int zkw_msm_bn254_g1(zkw_ctx* ctx, int which_bases, const uint64_t* bases, const uint64_t* scalars,
+                     size_t n, uint64_t out_xyz[12]);
+/* Device-pointer variant: scalars_dev (and bases_dev for ZKW_BASES_CALLER) are device pointers;
+ * out_xyz_dev receives 12 u64 on the device; asynchronous on the ctx stream. */
+int zkw_msm_bn254_g1_dev(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev,
+                         const uint64_t* scalars_dev, size_t n, uint64_t* out_xyz_dev);
+/* Jacobian -> affine (x,y) Montgomery, (0,0) for the identity: C::Curve::batch_normalize. */
+int zkw_g1_batch_normalize(zkw_ctx* ctx, const uint64_t* xyz /* m*12 */, size_t m, uint64_t* out_xy /* m*8 */);
+
+/* ---- NTT: halo2_proofs::arithmetic::best_fft(a, omega, log_n) ------------------------------ */
+/* In place, natural order in and out: a[i] <- sum_j a[j] * omega^(i*j).  scale_or_null, if
+ * given, multiplies every output (n^-1 for an inverse transform). */
+int zkw_ntt_bn254_fr(zkw_ctx* ctx, uint64_t* a /* 2^log_n * 4 */, unsigned log_n, const uint64_t omega[4],
+                     const uint64_t* scale_or_null);
+int zkw_ntt_bn254_fr_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned log_n, const uint64_t omega[4],
+                         const uint64_t* scale_or_null);
+
+/* ---- EvaluationDomain mirrors (k = log2 rows, ext_k = log2 extended rows) --------------------- */
+/* lagrange_to_coeff: inverse NTT over the 2^k domain, scaled by n^-1; in place. */
+int zkw_lagrange_to_coeff(zkw_ctx* ctx, uint64_t* a, unsigned k);
+int zkw_lagrange_to_coeff_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned k);
+/* coeff_to_lagrange: forward NTT over the 2^k domain; in place. */
+int zkw_coeff_to_lagrange(zkw_ctx* ctx, uint64_t* a, unsigned k);
+int zkw_coeff_to_lagrange_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned k);
+/* coeff_to_extended: a_i *= zeta^(i mod 3), zero-pad 2^k -> 2^ext_k, forward NTT with the
+ * extended root.  coeffs: 2^k*4 u64; out: 2^ext_k*4 u64 (must not alias coeffs). */
+int zkw_coeff_to_extended(zkw_ctx* ctx, const uint64_t* coeffs, unsigned k, unsigned ext_k, uint64_t* out);
+int zkw_coeff_to_extended_dev(zkw_ctx* ctx, const uint64_t* coeffs_dev, unsigned k, unsigned ext_k, uint64_t* out_dev);
+/* extended_to_coeff: inverse NTT over 2^ext_k, scale by 2^-ext_k, a_i *= zeta^-(i mod 3); in
+ * place over all 2^ext_k entries (upstream then truncates to n*(degree-1); the caller does). */
+int zkw_extended_to_coeff(zkw_ctx* ctx, uint64_t* a, unsigned ext_k);
+int zkw_extended_to_coeff_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned ext_k);
+
+/* ---- quotient: Evaluator::evaluate_h + divide_by_vanishing_poly for the ECDSA circuit ------- */
+/* Shape of halo2-lib's FlexGate + Range configuration as instantiated by
+ * ECDSACircuit::configure (ecdsa_p256.rs:94-115) from the JSON configs
+ * (halo2-circuits/src/configs/ *.config files).  The constraint list is the one the reference's
+ * generated verifier checks (proving-server/P256Verifier.yul:406-547):
+ *   gates      : for each gate advice column c:  q_c * (a_c(X) + a_c(wX)*a_c(w^2X) - a_c(w^3X))
+ *   permutation: columns [constants.., gate advice.., lookup advice..], chunks of cs_degree-2
+ *   lookups    : one per lookup advice column: (a_l ; table), or — selector mode, when
+ *                num_lookup_advice == 0 — a single lookup (q_lookup * a_0 ; table).           */
+typedef struct {
+    uint32_t k;                  /* log2 rows                                                 */
+    uint32_t ext_k;              /* log2 extended rows (k+2 for every config of the reference)  */
+    uint32_t num_advice;         /* gate advice columns A                                     */
+    uint32_t num_lookup_advice;  /* dedicated lookup advice columns L; 0 = selector mode       */
+    uint32_t num_fixed;          /* constant (fixed, equality-enabled) columns F              */
+    uint32_t blinding_factors;   /* cs.blinding_factors(); 6 for this circuit (yul:309-323)      */
+    uint32_t cs_degree;          /* cs.degree(): 4 (plain lookup input) or 5 (selector mode)    */
+    uint32_t reserved;
+} zkw_circuit_shape;
+
+static inline uint32_t zkw_shape_perm_columns(const zkw_circuit_shape* s) {
+    return s->num_fixed + s->num_advice + s->num_lookup_advice;
+}
+static inline uint32_t zkw_shape_perm_sets(const zkw_circuit_shape* s) {
+    uint32_t chunk = s->cs_degree - 2;
+    return (zkw_shape_perm_columns(s) + chunk - 1) / chunk;
+}
+static inline uint32_t zkw_shape_lookups(const zkw_circuit_shape* s) {
+    return s->num_lookup_advice ? s->num_lookup_advice : 1;
+}
+
+/* Every pointer is a 2^ext_k * 4 u64 evaluation vector over the extended coset zeta*<w_ext>
+ * (what coeff_to_extended returns), except the four challenges.  Arrays of pointers are indexed
+ * as the comments say.  For the `_dev` entry point all vectors are device pointers (the pointer
+ * TABLES themselves stay in host memory). */
+typedef struct {
+    zkw_circuit_shape shape;
+    const uint64_t* const* advice;        /* [A + L]  gate advice then lookup advice            */
+    const uint64_t* const* constants;     /* [F]                                               */
+    const uint64_t* table;                /* range-lookup table column                         */
+    const uint64_t* const* q_enable;      /* [A]      gate selectors                           */
+    const uint64_t* q_lookup;             /* selector mode only, else NULL                     */
+    const uint64_t* const* sigma;         /* [F + A + L] permutation cosets, permutation order */
+    const uint64_t* const* perm_z;        /* [perm_sets] grand products                        */
+    const uint64_t* const* lookup_z;      /* [lookups]                                         */
+    const uint64_t* const* lookup_a;      /* [lookups] permuted input  A'                      */
+    const uint64_t* const* lookup_s;      /* [lookups] permuted table  S'                      */
+    const uint64_t* l0;
+    const uint64_t* l_last;
+    const uint64_t* l_active;             /* 1 - (l_last + l_blind)                            */
+    uint64_t y[4], beta[4], gamma[4], theta[4];  /* Montgomery form                           */
+} zkw_quotient_inputs;
+
+/* h_ext[i] = ( sum_j y^(m-1-j) C_j(row i) ) / ((zeta*w_ext^i)^n - 1), 2^ext_k * 4 u64. */
+int zkw_quotient_ecdsa(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext);
+int zkw_quotient_ecdsa_dev(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext_dev);
+
+/* ---- device memory helpers for FFI callers that keep polynomials resident -------------------- */
+int zkw_dev_alloc(zkw_ctx* ctx, size_t bytes, void** out_dev);
+int zkw_dev_free(zkw_ctx* ctx, void* dev);
+int zkw_memcpy_h2d(zkw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int zkw_memcpy_d2h(zkw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZKW_B200_H */
