@@ -69,18 +69,30 @@ uint64_t zkw_ctx_launch_count(zkw_ctx* ctx);
 /* Copies n affine points of each basis to the device once; later MSMs name them by id. */
 int zkw_srs_load(zkw_ctx* ctx, const uint64_t* g /* n*8 */, const uint64_t* g_lagrange /* n*8 or NULL */, size_t n);
 
+/* Same, from device arrays (the context keeps its own copies). */
+int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagrange_dev, size_t n);
+/* MSM tuning, effective for bases loaded afterwards: window_bits 0 = automatic; precompute != 0 keeps
+ * 2^(c*w)*P_i for every window of the resident bases (c.f. msm.cu). Environment overrides at ctx
+ * creation: ZKW_MSM_WINDOW_BITS, ZKW_MSM_PRECOMPUTE. */
+int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute);
+
 enum { ZKW_BASES_G = 0, ZKW_BASES_G_LAGRANGE = 1, ZKW_BASES_CALLER = 2 };
 
 /* ---- MSM: halo2_proofs::arithmetic::best_multiexp(coeffs, bases) -> C::Curve -------------- */
 /* scalars: n*4 u64, Montgomery form as stored by halo2curves (the kernel de-Montgomerises,
  * the analogue of upstream's `to_repr()`).  bases: n*8 u64 when which_bases == ZKW_BASES_CALLER,
- * else ignored.  out_xyz: Jacobian (X,Y,Z) Montgomery, identity => Z = 0. */
+ * else ignored.  out_xyz: Jacobian (X,Y,Z) Montgomery, identity => Z = 0.  The representative
+ * returned is the normalised one, (x, y, 1), so the bytes are deterministic. */
 int zkw_msm_bn254_g1(zkw_ctx* ctx, int which_bases, const uint64_t* bases, const uint64_t* scalars,
                      size_t n, uint64_t out_xyz[12]);
 /* Device-pointer variant: scalars_dev (and bases_dev for ZKW_BASES_CALLER) are device pointers;
  * out_xyz_dev receives 12 u64 on the device; asynchronous on the ctx stream. */
 int zkw_msm_bn254_g1_dev(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev,
                          const uint64_t* scalars_dev, size_t n, uint64_t* out_xyz_dev);
+/* scalars (and caller bases) on the device, result written to host memory; synchronises the ctx
+ * stream.  This is the form the prover pipeline uses: commitments feed the host-side transcript. */
+int zkw_msm_bn254_g1_dev_to_host(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev,
+                                 const uint64_t* scalars_dev, size_t n, uint64_t out_xyz[12]);
 /* Jacobian -> affine (x,y) Montgomery, (0,0) for the identity: C::Curve::batch_normalize. */
 int zkw_g1_batch_normalize(zkw_ctx* ctx, const uint64_t* xyz /* m*12 */, size_t m, uint64_t* out_xy /* m*8 */);
 

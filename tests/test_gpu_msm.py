@@ -1,0 +1,148 @@
+"""GPU parity: zkw_msm_bn254_g1 vs the CPU oracle's best_multiexp restatement (compared after affine
+normalisation: the only canonical form of a projective result).
+
+best_multiexp is reached by the reference through ParamsKZG::commit{,_lagrange} inside create_proof /
+keygen (halo2-circuits/src/ecc/ecdsa_p256.rs:259-260, 366-373, 416-423, 555-562).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bases(oracle, n, seed):
+    return oracle.g1_fixed_base_mul(oracle.fr_random(n, seed))
+
+
+def _affine(oracle, xyz):
+    return oracle.g1_to_affine(np.asarray(xyz).reshape(1, 12))[0]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 100, 1000, 4097, 1 << 13, (1 << 14) + 7, 1 << 16])
+def test_msm_caller_bases_matches_oracle(ctx, oracle, n):
+    s = oracle.fr_random(n, 1000 + n)
+    b = _bases(oracle, n, 2000 + n)
+    got = ctx.msm(s, b)
+    want = oracle.best_multiexp(s, b)
+    assert np.array_equal(_affine(oracle, got), _affine(oracle, want))
+    # the ABI returns the normalised representative (x, y, 1)
+    assert np.array_equal(got[:8], _affine(oracle, want))
+
+
+def test_msm_small_against_python_naive(ctx, oracle):
+    from oracle import pyref as pr
+    n = 12
+    s = oracle.fr_random(n, 5)
+    b = _bases(oracle, n, 6)
+    got = oracle.g1_affine_to_ints(_affine(oracle, ctx.msm(s, b)))
+    want = pr.msm_naive(oracle.fr_from_mont(s), [oracle.g1_affine_to_ints(x) for x in b])
+    assert got == want
+
+
+def test_msm_edge_scalars(ctx, oracle):
+    from oracle import pyref as pr
+    n = 2048
+    b = _bases(oracle, n, 77)
+    zero = np.zeros((n, 4), dtype=np.uint64)
+    out = ctx.msm(zero, b)
+    assert not out[8:].any()  # identity: Z = 0
+    for val in (1, 2, pr.R - 1, (1 << 128) - 1, 1 << 253, (pr.R - 1) // 2):
+        s = np.tile(oracle.fr_to_mont([val])[0], (n, 1))
+        assert np.array_equal(_affine(oracle, ctx.msm(s, b)), _affine(oracle, oracle.best_multiexp(s, b))), hex(val)
+    # witness-like skew: mostly zeros and bits, a few small limbs
+    rng = np.random.default_rng(3)
+    vals = [int(v) for v in rng.choice([0, 0, 0, 1, 1, 2, 3, (1 << 88) - 1, 1 << 64], size=n)]
+    s = oracle.fr_to_mont(vals)
+    assert np.array_equal(_affine(oracle, ctx.msm(s, b)), _affine(oracle, oracle.best_multiexp(s, b)))
+
+
+def test_msm_edge_bases(ctx, oracle):
+    n = 512
+    s = oracle.fr_random(n, 91)
+    b = _bases(oracle, n, 92)
+    b[5] = 0            # identity point (0,0)
+    b[100] = b[7]       # duplicate base
+    b[200:264] = b[9]   # a run of equal bases
+    s[200:264] = s[9]   # ... with equal scalars: forces the doubling branch inside a bucket
+    assert np.array_equal(_affine(oracle, ctx.msm(s, b)), _affine(oracle, oracle.best_multiexp(s, b)))
+    # P and -P with the same scalar cancel
+    from oracle import pyref as pr
+    neg = b[:2].copy()
+    p = oracle.g1_affine_to_ints(b[0])
+    neg[1] = oracle.g1_ints_to_affine((p[0], (-p[1]) % pr.P))
+    neg[0] = b[0]
+    out = ctx.msm(np.tile(s[0], (2, 1)), neg)
+    assert not out[8:].any()
+
+
+@pytest.mark.parametrize("n", [1 << 10, 1 << 14, 1 << 16])
+def test_msm_resident_srs_with_window_tables(zkw, oracle, n):
+    """zkw_srs_load keeps g / g_lagrange on the device with their window tables; MSMs name them by id."""
+    c = zkw.Context(0)
+    try:
+        g = _bases(oracle, n, 31)
+        gl = _bases(oracle, n, 32)
+        c.srs_load(g, gl)
+        s = oracle.fr_random(n, 33)
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s, g)))
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G_LAGRANGE)[:8], _affine(oracle, oracle.best_multiexp(s, gl)))
+        # a shorter MSM against a prefix of the resident basis (commit of a low-degree polynomial)
+        m = n // 2 + 3
+        assert np.array_equal(c.msm(s[:m], which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s[:m], g[:m])))
+        # without tables (per-window bucket groups) the answer is the same
+        c.msm_config(window_bits=0, precompute=False)
+        c.srs_load(g, None)
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s, g)))
+    finally:
+        c.close()
+
+
+def test_msm_before_srs_load_is_an_error(zkw, oracle):
+    c = zkw.Context(0)
+    try:
+        with pytest.raises(zkw.ZkwError) as ei:
+            c.msm(oracle.fr_random(4, 1), which=zkw.BASES_G)
+        assert ei.value.status == -5
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("c_bits", [4, 7, 11, 13, 16])
+def test_msm_window_sizes(zkw, oracle, c_bits):
+    c = zkw.Context(0)
+    try:
+        c.msm_config(window_bits=c_bits, precompute=True)
+        n = 3000
+        s = oracle.fr_random(n, 55)
+        b = _bases(oracle, n, 56)
+        want = _affine(oracle, oracle.best_multiexp(s, b))
+        assert np.array_equal(c.msm(s, b)[:8], want)
+        c.srs_load(b, None)
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], want)
+    finally:
+        c.close()
+
+
+def test_msm_full_size_split_identity_k19(zkw, oracle):
+    """BASELINE size (2^19 points, resident SRS with window tables): the oracle needs minutes there,
+    so check size-independent properties — msm(whole) = msm(low half) + msm(high half) with the halves
+    taken through the other code path (prefix of the resident basis / caller bases), and one oracle run
+    on a 2^16 prefix."""
+    import ctypes as C
+    n = 1 << 19
+    c = zkw.Context(0)
+    try:
+        g = _bases(oracle, n, 61)
+        c.srs_load(g, None)
+        a = oracle.fr_random(n, 62)
+        whole = c.msm(a, which=zkw.BASES_G)
+        m = 1 << 16
+        assert np.array_equal(c.msm(a[:m], which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(a[:m], g[:m])))
+        lo = c.msm(a[: n // 2], which=zkw.BASES_G)
+        hi = c.msm(a[n // 2:], g[n // 2:])
+        s = np.empty(12, dtype=np.uint64)
+        u64p = C.POINTER(C.c_uint64)
+        oracle.lib().zko_g1_add(s.ctypes.data_as(u64p), lo.ctypes.data_as(u64p), hi.ctypes.data_as(u64p))
+        assert np.array_equal(_affine(oracle, s), whole[:8])
+    finally:
+        c.close()

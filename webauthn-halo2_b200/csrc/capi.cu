@@ -1,0 +1,425 @@
+// capi.cu — the extern "C" surface declared in include/zkw_b200.h: context, SRS residency, and the
+// host-pointer / device-pointer entry points a patched halo2_proofs binds in place of best_multiexp,
+// best_fft, EvaluationDomain::{lagrange_to_coeff, coeff_to_extended, extended_to_coeff} and
+// evaluate_h (call sites in the reference: halo2-circuits/src/ecc/ecdsa_p256.rs:259-260, 366-373,
+// 416-423, 555-562).  No CPU fallback lives here: every path ends in a kernel launch or an error.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include "common.cuh"
+
+namespace zkw {
+
+int set_cuda_error(zkw_ctx* ctx, cudaError_t e, const char* what) {
+    if (ctx) {
+        ctx->last_err = std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    }
+    cudaGetLastError();  // clear the sticky-less error state
+    if (e == cudaErrorMemoryAllocation) return ZKW_ERR_OOM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) return ZKW_ERR_NO_DEVICE;
+    return ZKW_ERR_CUDA;
+}
+
+int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes) {
+    if (b.bytes >= bytes && b.ptr) return ZKW_OK;
+    if (b.ptr) {
+        // the old area may still be in use by queued work
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaStreamSynchronize");
+        cudaFree(b.ptr);
+        b.ptr = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    cudaError_t e = cudaMalloc(&b.ptr, want);
+    if (e != cudaSuccess) { b.ptr = nullptr; return set_cuda_error(ctx, e, "cudaMalloc"); }
+    b.bytes = want;
+    return ZKW_OK;
+}
+
+// ---- host-side domain constants (EvaluationDomain::new restated with the device field class) ----
+static Fr fr_pow_host(Fr b, uint64_t e) { return b.pow(e); }
+
+void domain_consts(unsigned k, unsigned ext_k, DomainConsts* out) {
+    static std::mutex mu;
+    static std::map<std::pair<unsigned, unsigned>, DomainConsts> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(k, ext_k);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return; }
+    // ROOT_OF_UNITY = 7^((r-1)/2^28), ZETA = 7^((r-1)/3), Montgomery form
+    static const uint64_t root_m[4] = {0x9632c7c5b639feb8ULL, 0x985ce3400d0ff299ULL, 0xb2dd880001b0ecd8ULL, 0x1d69070d6d98ce29ULL};
+    static const uint64_t zeta_m[4] = {0x93e7cede4a0329b3ULL, 0x7d4fdca77a96c167ULL, 0x8be4ba08b19a750aULL, 0x1cbd5653a5661c25ULL};
+    DomainConsts d;
+    memset(&d, 0, sizeof(d));
+    d.k = k; d.ext_k = ext_k;
+    Fr w; memcpy(w.l, root_m, 32);
+    for (unsigned i = ext_k; i < 28; i++) w = w.sqr();
+    Fr ext_omega = w;
+    for (unsigned i = k; i < ext_k; i++) w = w.sqr();
+    Fr omega = w;
+    Fr zeta; memcpy(zeta.l, zeta_m, 32);
+    Fr zeta_inv = zeta.sqr();
+    Fr two = Fr::one() + Fr::one();
+    Fr n_inv = fr_pow_host(two, k).inv(), en_inv = fr_pow_host(two, ext_k).inv();
+    Fr omega_inv = omega.inv(), ext_omega_inv = ext_omega.inv();
+    memcpy(d.omega, omega.l, 32); memcpy(d.omega_inv, omega_inv.l, 32);
+    memcpy(d.ext_omega, ext_omega.l, 32); memcpy(d.ext_omega_inv, ext_omega_inv.l, 32);
+    memcpy(d.zeta, zeta.l, 32); memcpy(d.zeta_inv, zeta_inv.l, 32);
+    memcpy(d.n_inv, n_inv.l, 32); memcpy(d.ext_n_inv, en_inv.l, 32);
+    Fr s1 = en_inv * zeta_inv, s2 = en_inv * zeta;  // zeta^-1 = zeta^2, zeta^-2 = zeta
+    memcpy(d.ext_scale3, en_inv.l, 32); memcpy(d.ext_scale3 + 4, s1.l, 32); memcpy(d.ext_scale3 + 8, s2.l, 32);
+    for (int i = 0; i < 3; i++) memcpy(d.n_scale3 + 4 * i, n_inv.l, 32);
+    unsigned m = 1u << (ext_k - k);
+    Fr cur = zeta;
+    for (unsigned i = 0; i < m && i < 16; i++) {
+        Fr t = fr_pow_host(cur, 1ull << k) - Fr::one();
+        Fr ti = t.inv();
+        memcpy(d.t_evals[i], ti.l, 32);
+        cur = cur * ext_omega;
+    }
+    cache[key] = d;
+    *out = d;
+}
+
+static int free_buffer(DeviceBuffer& b) {
+    if (b.ptr) cudaFree(b.ptr);
+    b.ptr = nullptr;
+    b.bytes = 0;
+    return 0;
+}
+
+}  // namespace zkw
+
+using namespace zkw;
+
+#define CTX_ENTER(ctx)                                             \
+    if (!(ctx)) return ZKW_ERR_INVALID;                            \
+    ZKW_CUDA(ctx, cudaSetDevice((ctx)->device))
+
+// host round trip shared by the host-pointer transforms
+template <class F>
+static int host_transform(zkw_ctx* ctx, const uint64_t* src, size_t n_in, uint64_t* dst, size_t n_out, F&& run) {
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, n_in * 32));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, src, n_in * 32, cudaMemcpyHostToDevice, ctx->stream));
+    uint64_t* out_dev = (uint64_t*)ctx->io_a.ptr;
+    if (n_out != n_in) {
+        ZKW_TRY(ensure_buffer(ctx, ctx->io_b, n_out * 32));
+        out_dev = (uint64_t*)ctx->io_b.ptr;
+    }
+    ZKW_TRY(run((uint64_t*)ctx->io_a.ptr, out_dev));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(dst, out_dev, n_out * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+
+extern "C" {
+
+const char* zkw_strerror(int status) {
+    switch (status) {
+        case ZKW_OK: return "ok";
+        case ZKW_ERR_NO_DEVICE: return "no usable CUDA device (there is no CPU fallback)";
+        case ZKW_ERR_CUDA: return "CUDA runtime error";
+        case ZKW_ERR_INVALID: return "invalid argument";
+        case ZKW_ERR_OOM: return "out of device memory";
+        case ZKW_ERR_STATE: return "invalid state (SRS not loaded?)";
+        case ZKW_ERR_UNSUPPORTED: return "unsupported circuit shape";
+        default: return "unknown status";
+    }
+}
+
+int zkw_ctx_create(int device, zkw_ctx** out) {
+    if (!out) return ZKW_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) { cudaGetLastError(); return ZKW_ERR_NO_DEVICE; }
+    if (device < 0 || device >= count) return ZKW_ERR_NO_DEVICE;
+    zkw_ctx* ctx = new zkw_ctx();
+    ctx->device = device;
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { int rc = set_cuda_error(ctx, e, "ctx init"); delete ctx; return rc; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    const char* env = getenv("ZKW_MSM_WINDOW_BITS");
+    if (env) ctx->msm_window_bits = atoi(env);
+    env = getenv("ZKW_MSM_PRECOMPUTE");
+    if (env) ctx->msm_precompute = atoi(env);
+    *out = ctx;
+    return ZKW_OK;
+}
+
+void zkw_ctx_destroy(zkw_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->twiddles) free_buffer(kv.second);
+    free_buffer(ctx->ntt_scratch); free_buffer(ctx->msm_ws);
+    free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table);
+    msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int zkw_ctx_sync(zkw_ctx* ctx) {
+    CTX_ENTER(ctx);
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+void* zkw_ctx_stream(zkw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+const char* zkw_last_cuda_error(zkw_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+uint64_t zkw_ctx_launch_count(zkw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute) {
+    if (!ctx || window_bits < 0 || window_bits > 20 || window_bits == 1) return ZKW_ERR_INVALID;
+    ctx->msm_window_bits = window_bits;
+    ctx->msm_precompute = precompute ? 1 : 0;
+    return ZKW_OK;
+}
+
+int zkw_dev_alloc(zkw_ctx* ctx, size_t bytes, void** out_dev) {
+    CTX_ENTER(ctx);
+    if (!out_dev) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaMalloc(out_dev, bytes ? bytes : 1));
+    return ZKW_OK;
+}
+int zkw_dev_free(zkw_ctx* ctx, void* dev) {
+    CTX_ENTER(ctx);
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKW_CUDA(ctx, cudaFree(dev));
+    return ZKW_OK;
+}
+int zkw_memcpy_h2d(zkw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    CTX_ENTER(ctx);
+    ZKW_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+int zkw_memcpy_d2h(zkw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    CTX_ENTER(ctx);
+    ZKW_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+// ---- SRS ----------------------------------------------------------------------------------------
+static int load_basis(zkw_ctx* ctx, MsmBasis& b, const uint64_t* host, size_t n) {
+    msm_free_basis(b);
+    if (!host) return ZKW_OK;
+    ZKW_CUDA(ctx, cudaMalloc((void**)&b.points, n * 64));
+    b.n = n;
+    ZKW_CUDA(ctx, cudaMemcpyAsync(b.points, host, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_TRY(msm_prepare_basis(ctx, b));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+int zkw_srs_load(zkw_ctx* ctx, const uint64_t* g, const uint64_t* g_lagrange, size_t n) {
+    CTX_ENTER(ctx);
+    if (!g || n == 0) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKW_TRY(load_basis(ctx, ctx->bases[ZKW_BASES_G], g, n));
+    ZKW_TRY(load_basis(ctx, ctx->bases[ZKW_BASES_G_LAGRANGE], g_lagrange, n));
+    return ZKW_OK;
+}
+
+// Device-resident variant: adopt copies of device arrays (used by the prover when the SRS was
+// generated on the device).
+int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagrange_dev, size_t n) {
+    CTX_ENTER(ctx);
+    if (!g_dev || n == 0) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t* srcs[2] = {g_dev, g_lagrange_dev};
+    for (int i = 0; i < 2; i++) {
+        MsmBasis& b = ctx->bases[i];
+        msm_free_basis(b);
+        if (!srcs[i]) continue;
+        ZKW_CUDA(ctx, cudaMalloc((void**)&b.points, n * 64));
+        b.n = n;
+        ZKW_CUDA(ctx, cudaMemcpyAsync(b.points, srcs[i], n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+        ZKW_TRY(msm_prepare_basis(ctx, b));
+    }
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+// ---- MSM ------------------------------------------------------------------------------------------
+int zkw_msm_bn254_g1_dev(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
+                         uint64_t* out_xyz_dev) {
+    CTX_ENTER(ctx);
+    if (!scalars_dev || !out_xyz_dev) return ZKW_ERR_INVALID;
+    uint64_t out[12];
+    ZKW_TRY(msm_run(ctx, which_bases, bases_dev, scalars_dev, n, out));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out_xyz_dev, out, 96, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+// scalars on the device, result on the host: what the prover pipeline uses (commitments go into
+// the transcript on the host)
+int zkw_msm_bn254_g1_dev_to_host(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev,
+                                 size_t n, uint64_t out_xyz[12]) {
+    CTX_ENTER(ctx);
+    if (!scalars_dev || !out_xyz) return ZKW_ERR_INVALID;
+    return msm_run(ctx, which_bases, bases_dev, scalars_dev, n, out_xyz);
+}
+
+int zkw_msm_bn254_g1(zkw_ctx* ctx, int which_bases, const uint64_t* bases, const uint64_t* scalars, size_t n,
+                     uint64_t out_xyz[12]) {
+    CTX_ENTER(ctx);
+    if (!scalars || !out_xyz) return ZKW_ERR_INVALID;
+    if (which_bases == ZKW_BASES_CALLER && !bases) return ZKW_ERR_INVALID;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, n * 32 + 32));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const uint64_t* bases_dev = nullptr;
+    if (which_bases == ZKW_BASES_CALLER) {
+        ZKW_TRY(ensure_buffer(ctx, ctx->io_b, n * 64 + 64));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_b.ptr, bases, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+        bases_dev = (const uint64_t*)ctx->io_b.ptr;
+    }
+    return msm_run(ctx, which_bases, bases_dev, (const uint64_t*)ctx->io_a.ptr, n, out_xyz);
+}
+
+int zkw_g1_batch_normalize(zkw_ctx* ctx, const uint64_t* xyz, size_t m, uint64_t* out_xy) {
+    CTX_ENTER(ctx);
+    if ((!xyz || !out_xy) && m) return ZKW_ERR_INVALID;
+    if (m == 0) return ZKW_OK;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, m * 96));
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_b, m * 64));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, xyz, m * 96, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_TRY(g1_batch_normalize_dev(ctx, (const uint64_t*)ctx->io_a.ptr, m, (uint64_t*)ctx->io_b.ptr));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->io_b.ptr, m * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+// ---- NTT --------------------------------------------------------------------------------------------
+int zkw_ntt_bn254_fr_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned log_n, const uint64_t omega[4], const uint64_t* scale_or_null) {
+    CTX_ENTER(ctx);
+    if (!a_dev || !omega) return ZKW_ERR_INVALID;
+    uint64_t s3[12];
+    if (scale_or_null) for (int i = 0; i < 3; i++) memcpy(s3 + 4 * i, scale_or_null, 32);
+    return ntt_run(ctx, a_dev, log_n, a_dev, log_n, omega, false, scale_or_null ? s3 : nullptr);
+}
+
+int zkw_ntt_bn254_fr(zkw_ctx* ctx, uint64_t* a, unsigned log_n, const uint64_t omega[4], const uint64_t* scale_or_null) {
+    CTX_ENTER(ctx);
+    if (!a || !omega || log_n > 28) return ZKW_ERR_INVALID;
+    const size_t n = (size_t)1 << log_n;
+    return host_transform(ctx, a, n, a, n, [&](uint64_t* in, uint64_t*) { return zkw_ntt_bn254_fr_dev(ctx, in, log_n, omega, scale_or_null); });
+}
+
+int zkw_lagrange_to_coeff_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned k) {
+    CTX_ENTER(ctx);
+    if (!a_dev || k > 28) return ZKW_ERR_INVALID;
+    DomainConsts dc;
+    domain_consts(k, k, &dc);
+    return ntt_run(ctx, a_dev, k, a_dev, k, dc.omega_inv, false, dc.n_scale3);
+}
+int zkw_lagrange_to_coeff(zkw_ctx* ctx, uint64_t* a, unsigned k) {
+    CTX_ENTER(ctx);
+    if (!a || k > 28) return ZKW_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    return host_transform(ctx, a, n, a, n, [&](uint64_t* in, uint64_t*) { return zkw_lagrange_to_coeff_dev(ctx, in, k); });
+}
+int zkw_coeff_to_lagrange_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned k) {
+    CTX_ENTER(ctx);
+    if (!a_dev || k > 28) return ZKW_ERR_INVALID;
+    DomainConsts dc;
+    domain_consts(k, k, &dc);
+    return ntt_run(ctx, a_dev, k, a_dev, k, dc.omega, false, nullptr);
+}
+int zkw_coeff_to_lagrange(zkw_ctx* ctx, uint64_t* a, unsigned k) {
+    CTX_ENTER(ctx);
+    if (!a || k > 28) return ZKW_ERR_INVALID;
+    const size_t n = (size_t)1 << k;
+    return host_transform(ctx, a, n, a, n, [&](uint64_t* in, uint64_t*) { return zkw_coeff_to_lagrange_dev(ctx, in, k); });
+}
+int zkw_coeff_to_extended_dev(zkw_ctx* ctx, const uint64_t* coeffs_dev, unsigned k, unsigned ext_k, uint64_t* out_dev) {
+    CTX_ENTER(ctx);
+    if (!coeffs_dev || !out_dev || ext_k > 28 || k > ext_k || (const void*)coeffs_dev == (const void*)out_dev) return ZKW_ERR_INVALID;
+    DomainConsts dc;
+    domain_consts(k, ext_k, &dc);
+    return ntt_run(ctx, coeffs_dev, k, out_dev, ext_k, dc.ext_omega, true, nullptr);
+}
+int zkw_coeff_to_extended(zkw_ctx* ctx, const uint64_t* coeffs, unsigned k, unsigned ext_k, uint64_t* out) {
+    CTX_ENTER(ctx);
+    if (!coeffs || !out || ext_k > 28 || k > ext_k) return ZKW_ERR_INVALID;
+    const size_t n_in = (size_t)1 << k, n_out = (size_t)1 << ext_k;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, n_in * 32));
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_b, n_out * 32));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, coeffs, n_in * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_TRY(zkw_coeff_to_extended_dev(ctx, (const uint64_t*)ctx->io_a.ptr, k, ext_k, (uint64_t*)ctx->io_b.ptr));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_b.ptr, n_out * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+int zkw_extended_to_coeff_dev(zkw_ctx* ctx, uint64_t* a_dev, unsigned ext_k) {
+    CTX_ENTER(ctx);
+    if (!a_dev || ext_k > 28) return ZKW_ERR_INVALID;
+    DomainConsts dc;
+    domain_consts(ext_k, ext_k, &dc);
+    return ntt_run(ctx, a_dev, ext_k, a_dev, ext_k, dc.ext_omega_inv, false, dc.ext_scale3);
+}
+int zkw_extended_to_coeff(zkw_ctx* ctx, uint64_t* a, unsigned ext_k) {
+    CTX_ENTER(ctx);
+    if (!a || ext_k > 28) return ZKW_ERR_INVALID;
+    const size_t n = (size_t)1 << ext_k;
+    return host_transform(ctx, a, n, a, n, [&](uint64_t* in, uint64_t*) { return zkw_extended_to_coeff_dev(ctx, in, ext_k); });
+}
+
+// ---- quotient ------------------------------------------------------------------------------------------
+int zkw_quotient_ecdsa_dev(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext_dev) {
+    CTX_ENTER(ctx);
+    if (!in || !h_ext_dev) return ZKW_ERR_INVALID;
+    return quotient_run(ctx, in, h_ext_dev);
+}
+
+int zkw_quotient_ecdsa(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext) {
+    CTX_ENTER(ctx);
+    if (!in || !h_ext) return ZKW_ERR_INVALID;
+    const zkw_circuit_shape& sh = in->shape;
+    if (sh.ext_k > 28) return ZKW_ERR_INVALID;
+    const unsigned A = sh.num_advice, L = sh.num_lookup_advice, F = sh.num_fixed;
+    const unsigned ncols = F + A + L, nsets = zkw_shape_perm_sets(&sh), nlk = zkw_shape_lookups(&sh);
+    if (L == 0 && !in->q_lookup) return ZKW_ERR_UNSUPPORTED;
+    const size_t en = (size_t)1 << sh.ext_k, vb = en * 32;
+    // stage every input coset in one device arena
+    std::vector<const uint64_t*> hosts;
+    auto add = [&](const uint64_t* const* t, unsigned cnt) { for (unsigned i = 0; i < cnt; i++) hosts.push_back(t ? t[i] : nullptr); };
+    add(in->advice, A + L); add(in->constants, F); add(in->q_enable, A); add(in->sigma, ncols);
+    add(in->perm_z, nsets); add(in->lookup_z, nlk); add(in->lookup_a, nlk); add(in->lookup_s, nlk);
+    hosts.push_back(in->table); hosts.push_back(in->l0); hosts.push_back(in->l_last); hosts.push_back(in->l_active);
+    if (L == 0) hosts.push_back(in->q_lookup);
+    for (auto p : hosts) if (!p) return ZKW_ERR_INVALID;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_c, (hosts.size() + 1) * vb));
+    char* arena = (char*)ctx->io_c.ptr;
+    std::vector<const uint64_t*> devs(hosts.size());
+    for (size_t i = 0; i < hosts.size(); i++) {
+        devs[i] = (const uint64_t*)(arena + i * vb);
+        ZKW_CUDA(ctx, cudaMemcpyAsync((void*)devs[i], hosts[i], vb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    uint64_t* h_dev = (uint64_t*)(arena + hosts.size() * vb);
+    zkw_quotient_inputs d = *in;
+    size_t o = 0;
+    d.advice = devs.data() + o; o += A + L;
+    d.constants = devs.data() + o; o += F;
+    d.q_enable = devs.data() + o; o += A;
+    d.sigma = devs.data() + o; o += ncols;
+    d.perm_z = devs.data() + o; o += nsets;
+    d.lookup_z = devs.data() + o; o += nlk;
+    d.lookup_a = devs.data() + o; o += nlk;
+    d.lookup_s = devs.data() + o; o += nlk;
+    d.table = devs[o++]; d.l0 = devs[o++]; d.l_last = devs[o++]; d.l_active = devs[o++];
+    d.q_lookup = (L == 0) ? devs[o++] : nullptr;
+    ZKW_TRY(quotient_run(ctx, &d, h_dev));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(h_ext, h_dev, vb, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// common.cuh — context object and launch plumbing shared by the kernels behind include/zkw_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <map>
+#include <string>
+#include <vector>
+#include <array>
+#include "../../include/zkw_b200.h"
+#include "curve.cuh"
+
+namespace zkw {
+
+struct TwiddleKey {
+    std::array<uint64_t, 4> omega;
+    unsigned log_n;
+    bool operator<(const TwiddleKey& o) const {
+        if (log_n != o.log_n) return log_n < o.log_n;
+        return omega < o.omega;
+    }
+};
+
+struct DeviceBuffer {
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+// Precomputed window multiples of a fixed basis: table[w*n + i] = 2^(c*w) * P_i (affine).
+struct MsmBasis {
+    uint64_t* points = nullptr;  // n affine points as loaded
+    uint64_t* table = nullptr;   // windows*n affine points, or nullptr when precomputation is off
+    size_t n = 0;
+    int c = 0, windows = 0;
+};
+
+}  // namespace zkw
+
+struct zkw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_err;
+    uint64_t launches = 0;
+    int sm_count = 148;
+
+    // SRS residency
+    zkw::MsmBasis bases[2];
+    // MSM tuning: window bits (0 = automatic) and whether fixed bases get window tables
+    int msm_window_bits = 0;
+    int msm_precompute = 1;
+
+    // twiddle tables: omega^i for i < 2^(log_n-1), keyed by (omega, log_n)
+    std::map<zkw::TwiddleKey, zkw::DeviceBuffer> twiddles;
+    // reusable scratch areas (grown on demand, never shrunk)
+    zkw::DeviceBuffer ntt_scratch;
+    zkw::DeviceBuffer msm_ws;
+    zkw::DeviceBuffer io_a, io_b, io_c;  // staging for the host-pointer entry points
+    zkw::DeviceBuffer ptr_table;         // device copy of the quotient pointer tables
+    void* pinned = nullptr;              // small pinned host area for results
+    size_t pinned_bytes = 0;
+};
+
+namespace zkw {
+
+int set_cuda_error(zkw_ctx* ctx, cudaError_t e, const char* what);
+int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes);
+
+#define ZKW_CUDA(ctx, call)                                            \
+    do {                                                               \
+        cudaError_t _e = (call);                                       \
+        if (_e != cudaSuccess) return zkw::set_cuda_error(ctx, _e, #call); \
+    } while (0)
+
+#define ZKW_TRY(expr)            \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != ZKW_OK) return _rc; \
+    } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define ZKW_LAUNCHED(ctx)                                                   \
+    do {                                                                    \
+        (ctx)->launches++;                                                  \
+        cudaError_t _e = cudaGetLastError();                                \
+        if (_e != cudaSuccess) return zkw::set_cuda_error(ctx, _e, "kernel launch"); \
+    } while (0)
+
+// ---- entry points implemented per translation unit (device pointers, async on ctx->stream) ----
+// ntt.cu
+int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, const uint64_t** out_dev);
+// generic transform: dst (2^log_n) <- NTT_omega(src'), src' = src zero-extended from 2^src_log_n with
+// optional zeta^(i mod 3) pre-scaling (coset) ; optional per-(i mod 3) output scaling. src may equal dst.
+int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t* dst_dev, unsigned log_n,
+            const uint64_t omega[4], bool coset_in, const uint64_t* scale3 /* 3*4 u64 host, or NULL */);
+// msm.cu
+int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
+            uint64_t out_xyz_host[12]);
+int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
+void msm_free_basis(MsmBasis& b);
+int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);
+// quotient.cu
+int quotient_run(zkw_ctx* ctx, const zkw_quotient_inputs* in /* device vectors */, uint64_t* h_ext_dev);
+
+// domain constants (host side, Montgomery form), see domain.cpp
+struct DomainConsts {
+    unsigned k, ext_k;
+    uint64_t omega[4], omega_inv[4], ext_omega[4], ext_omega_inv[4];
+    uint64_t zeta[4], zeta_inv[4];            // g_coset, g_coset_inv (= zeta^2)
+    uint64_t n_inv[4], ext_n_inv[4];
+    uint64_t ext_scale3[12];                  // 2^-ext_k * zeta^-(i mod 3), i = 0,1,2
+    uint64_t n_scale3[12];                    // n^-1 replicated
+    uint64_t t_evals[16][4];                  // 1/((zeta*w_ext^i)^n - 1), i < 2^(ext_k-k)
+};
+void domain_consts(unsigned k, unsigned ext_k, DomainConsts* out);
+
+}  // namespace zkw

@@ -1,0 +1,338 @@
+// field.cuh — 254-bit Montgomery prime fields (BN254 Fr and Fq) in registers, for sm_100a.
+//
+// Device-side replacement for halo2curves::bn256::{Fr, Fq} (imported by the reference at
+// halo2-circuits/src/ecc/ecdsa_p256.rs:27; moduli = f_q / f_p of proving-server/P256Verifier.yul:17-18).
+// Memory format is halo2curves' own: [u64;4] little-endian limbs, Montgomery form with R = 2^256,
+// fully reduced — read here as 8 x u32 (same bytes) with two 128-bit loads per element.
+//
+// The product is a word-serial Montgomery multiplication over 32-bit limbs built from
+// mad.lo.cc / madc.hi.cc carry chains.  Partial products of even- and odd-indexed multiplicand
+// limbs are kept in two accumulators (A at limb offset 0, B at limb offset 1) so each row is one
+// uninterrupted carry chain; the per-row division by 2^32 swaps the roles of the accumulators
+// (A' = B + A[1], B' = A >> 64) and is folded into the next row's chain.  No tensor cores: this is
+// integer modular arithmetic.
+#pragma once
+#include <stdint.h>
+
+namespace zkw {
+
+struct FrParams {
+    // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+    static __host__ __device__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static __host__ __device__ constexpr uint32_t one(int i) {  // R mod r
+        constexpr uint32_t m[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static __host__ __device__ constexpr uint32_t r2(int i) {  // R^2 mod r
+        constexpr uint32_t m[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xefffffffu;  // -r^-1 mod 2^32
+};
+
+struct FqParams {
+    // p = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+    static __host__ __device__ constexpr uint32_t mod(int i) {
+        constexpr uint32_t m[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u};
+        return m[i];
+    }
+    static __host__ __device__ constexpr uint32_t one(int i) {  // R mod p
+        constexpr uint32_t m[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u};
+        return m[i];
+    }
+    static __host__ __device__ constexpr uint32_t r2(int i) {  // R^2 mod p
+        constexpr uint32_t m[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u};
+        return m[i];
+    }
+    static constexpr uint32_t INV = 0xe4866389u;  // -p^-1 mod 2^32
+};
+
+// c[0..7] = {lo,hi} of x0*b, x1*b, x2*b, x3*b (no carries: the four products do not overlap)
+__device__ __forceinline__ void mul_pairs(uint32_t c[9], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("mul.lo.u32 %0, %8, %12;\n\t"
+        "mul.hi.u32 %1, %8, %12;\n\t"
+        "mul.lo.u32 %2, %9, %12;\n\t"
+        "mul.hi.u32 %3, %9, %12;\n\t"
+        "mul.lo.u32 %4, %10, %12;\n\t"
+        "mul.hi.u32 %5, %10, %12;\n\t"
+        "mul.lo.u32 %6, %11, %12;\n\t"
+        "mul.hi.u32 %7, %11, %12;"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    c[8] = 0;
+}
+
+// c[0..8] += x0*b + x1*b*2^64 + x2*b*2^128 + x3*b*2^192 as one carry chain
+__device__ __forceinline__ void mad_pairs(uint32_t c[9], uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0;\n\t"
+        "madc.hi.cc.u32 %1, %9, %13, %1;\n\t"
+        "madc.lo.cc.u32 %2, %10, %13, %2;\n\t"
+        "madc.hi.cc.u32 %3, %10, %13, %3;\n\t"
+        "madc.lo.cc.u32 %4, %11, %13, %4;\n\t"
+        "madc.hi.cc.u32 %5, %11, %13, %5;\n\t"
+        "madc.lo.cc.u32 %6, %12, %13, %6;\n\t"
+        "madc.hi.cc.u32 %7, %12, %13, %7;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8])
+        : "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+}
+
+// Row step of the two-accumulator scheme after a division by 2^32:
+//   nA0 = B0 + A1 (carry out), nB[k] = A[k+2] + (x_k * b pairs) + carry, k = 0..7 (A[9] == 0)
+__device__ __forceinline__ void shift_mad_pairs(uint32_t& nA0, uint32_t nB[9], uint32_t B0, const uint32_t A[9],
+                                                uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("add.cc.u32 %0, %9, %10;\n\t"
+        "madc.lo.cc.u32 %1, %18, %22, %11;\n\t"
+        "madc.hi.cc.u32 %2, %18, %22, %12;\n\t"
+        "madc.lo.cc.u32 %3, %19, %22, %13;\n\t"
+        "madc.hi.cc.u32 %4, %19, %22, %14;\n\t"
+        "madc.lo.cc.u32 %5, %20, %22, %15;\n\t"
+        "madc.hi.cc.u32 %6, %20, %22, %16;\n\t"
+        "madc.lo.cc.u32 %7, %21, %22, %17;\n\t"
+        "madc.hi.u32 %8, %21, %22, 0;"
+        : "=r"(nA0), "=r"(nB[0]), "=r"(nB[1]), "=r"(nB[2]), "=r"(nB[3]), "=r"(nB[4]), "=r"(nB[5]), "=r"(nB[6]), "=r"(nB[7])
+        : "r"(B0), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+          "r"(x0), "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    nB[8] = 0;
+}
+
+template <class P>
+struct Fp {
+    uint32_t l[8];
+
+    __host__ __device__ __forceinline__ static Fp zero() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = 0;
+        return r;
+    }
+    __host__ __device__ __forceinline__ static Fp one() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = P::one(i);
+        return r;
+    }
+    __host__ __device__ __forceinline__ static Fp r2() {
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = P::r2(i);
+        return r;
+    }
+    // two 128-bit loads / stores (element = 32 B, 16-B aligned at minimum)
+    __host__ __device__ __forceinline__ static Fp load(const void* p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 lo = q[0], hi = q[1];
+        Fp r;
+        r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+        r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+        return r;
+    }
+    __device__ __forceinline__ static Fp load_nc(const void* p) {  // read-only path
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 lo = __ldg(q), hi = __ldg(q + 1);
+        Fp r;
+        r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+        r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+        return r;
+    }
+    __host__ __device__ __forceinline__ void store(void* p) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = make_uint4(l[0], l[1], l[2], l[3]);
+        q[1] = make_uint4(l[4], l[5], l[6], l[7]);
+    }
+    __host__ __device__ __forceinline__ bool is_zero() const {
+        return (l[0] | l[1] | l[2] | l[3] | l[4] | l[5] | l[6] | l[7]) == 0;
+    }
+    __host__ __device__ __forceinline__ bool operator==(const Fp& o) const {
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) d |= l[i] ^ o.l[i];
+        return d == 0;
+    }
+    __host__ __device__ __forceinline__ bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // t = x - mod; returns borrow (1 if x < mod)
+    __host__ __device__ __forceinline__ static uint32_t sub_mod(uint32_t t[8], const uint32_t x[8]) {
+        uint32_t borrow;
+#ifndef __CUDA_ARCH__
+        int64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (int64_t)x[i] - (int64_t)P::mod(i); t[i] = (uint32_t)c; c >>= 32; }
+        borrow = (uint32_t)c;
+#else
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+            : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+              "r"(P::mod(0)), "r"(P::mod(1)), "r"(P::mod(2)), "r"(P::mod(3)), "r"(P::mod(4)), "r"(P::mod(5)), "r"(P::mod(6)), "r"(P::mod(7)));
+#endif
+        return borrow;  // 0xffffffff if borrowed, else 0
+    }
+    // x < 2*mod  ->  x mod mod
+    __host__ __device__ __forceinline__ void reduce_once() {
+        uint32_t t[8];
+        uint32_t borrow = sub_mod(t, l);
+#pragma unroll
+        for (int i = 0; i < 8; i++) l[i] = borrow ? l[i] : t[i];
+    }
+
+    __host__ __device__ __forceinline__ friend Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+#ifndef __CUDA_ARCH__
+        uint64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (uint64_t)a.l[i] + b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
+#else
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#endif
+        r.reduce_once();  // a,b < mod < 2^254: the sum cannot carry out of 256 bits
+        return r;
+    }
+    __host__ __device__ __forceinline__ friend Fp operator-(const Fp& a, const Fp& b) {
+        Fp r;
+        uint32_t borrow;
+#ifndef __CUDA_ARCH__
+        int64_t c = 0;
+        for (int i = 0; i < 8; i++) { c += (int64_t)a.l[i] - (int64_t)b.l[i]; r.l[i] = (uint32_t)c; c >>= 32; }
+        borrow = (uint32_t)c;
+        uint64_t d = 0;
+        for (int i = 0; i < 8; i++) { d += (uint64_t)r.l[i] + (P::mod(i) & borrow); r.l[i] = (uint32_t)d; d >>= 32; }
+#else
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]), "=r"(borrow)
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+        // add back mod & borrow-mask
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+            : "r"(P::mod(0) & borrow), "r"(P::mod(1) & borrow), "r"(P::mod(2) & borrow), "r"(P::mod(3) & borrow),
+              "r"(P::mod(4) & borrow), "r"(P::mod(5) & borrow), "r"(P::mod(6) & borrow), "r"(P::mod(7) & borrow));
+#endif
+        return r;
+    }
+    __host__ __device__ __forceinline__ Fp neg() const { return zero() - *this; }
+    __host__ __device__ __forceinline__ Fp dbl() const { return *this + *this; }
+
+    // Montgomery product a*b*R^-1 mod m, fully reduced.
+    __host__ __device__ __forceinline__ friend Fp operator*(const Fp& a, const Fp& b) {
+#ifndef __CUDA_ARCH__
+        // portable word-serial Montgomery product (host-side unit tests of the device formulas)
+        uint32_t t[10] = {0};
+        for (int i = 0; i < 8; i++) {
+            uint64_t c = 0;
+            for (int j = 0; j < 8; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
+            c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
+            uint32_t m = t[0] * P::INV;
+            c = (uint64_t)m * P::mod(0) + t[0]; c >>= 32;
+            for (int j = 1; j < 8; j++) { c += (uint64_t)m * P::mod(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
+            c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+        }
+        Fp r;
+        for (int i = 0; i < 8; i++) r.l[i] = t[i];
+        r.reduce_once();
+        return r;
+#else
+        uint32_t A[9], B[9];
+        mul_pairs(A, a.l[0], a.l[2], a.l[4], a.l[6], b.l[0]);
+        mul_pairs(B, a.l[1], a.l[3], a.l[5], a.l[7], b.l[0]);
+        uint32_t m = A[0] * P::INV;
+        mad_pairs(A, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+        mad_pairs(B, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            uint32_t nA[9], nB[9];
+            shift_mad_pairs(nA[0], nB, B[0], A, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+#pragma unroll
+            for (int k = 1; k < 9; k++) nA[k] = B[k];
+            mad_pairs(nA, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            m = nA[0] * P::INV;
+            mad_pairs(nA, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+            mad_pairs(nB, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+#pragma unroll
+            for (int k = 0; k < 9; k++) { A[k] = nA[k]; B[k] = nB[k]; }
+        }
+        Fp r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+              "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
+        r.reduce_once();
+        return r;
+#endif
+    }
+    __host__ __device__ __forceinline__ Fp sqr() const { return *this * *this; }
+
+    __host__ __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
+    __host__ __device__ __forceinline__ Fp from_mont() const {
+        Fp o = zero();
+        o.l[0] = 1;
+        return *this * o;
+    }
+
+    // a^e for a 64-bit exponent (square-and-multiply, MSB first)
+    __host__ __device__ Fp pow(uint64_t e) const {
+        Fp acc = one();
+        for (int i = 63; i >= 0; i--) {
+            acc = acc.sqr();
+            if ((e >> i) & 1) acc = acc * *this;
+        }
+        return acc;
+    }
+    // Fermat inverse a^(m-2); inverse of zero is zero.
+    __host__ __device__ Fp inv() const {
+        Fp acc = one();
+        for (int i = 7; i >= 0; i--) {
+            uint32_t w = P::mod(i) - (i == 0 ? 2u : 0u);
+            for (int b = 31; b >= 0; b--) {
+                acc = acc.sqr();
+                if ((w >> b) & 1) acc = acc * *this;
+            }
+        }
+        return acc;
+    }
+};
+
+using Fr = Fp<FrParams>;
+using Fq = Fp<FqParams>;
+
+}  // namespace zkw

@@ -1,0 +1,439 @@
+// msm.cu — multi-scalar multiplication over BN254 G1 for sm_100a: the device replacement of
+// halo2_proofs::arithmetic::best_multiexp (KZG commit / commit_lagrange), reached from the reference
+// through create_proof and keygen (halo2-circuits/src/ecc/ecdsa_p256.rs:259-260, 366-373, 416-423,
+// 555-562).  Result = sum_i s_i * P_i; only its affine normalisation is canonical, and that is what
+// the C ABI hands back (as Jacobian (x, y, 1)).
+//
+// Pippenger, re-laid-out for the GPU:
+//   recode     scalars leave Montgomery form (upstream's to_repr()) and are cut into W signed
+//              c-bit digits d in [-2^(c-1), 2^(c-1)]; |d| names a bucket, the sign negates the point.
+//   fixed SRS  for the resident bases (g, g_lagrange) the context holds 2^(c*w) * P_i for every
+//              window w, so all windows share ONE set of 2^(c-1) buckets and there is no per-window
+//              doubling chain at the end ("groups" G = 1).  Caller-supplied bases use one bucket set
+//              per window (G = W) and the windows are combined on the host.
+//   sort       counting sort of the (window, point) entries by bucket: histogram (atomics in L2),
+//              single-CTA scan, scatter.
+//   accumulate the sorted entry list is cut into bucket-aligned slices of <= kSlice entries; one
+//              thread sums one slice with mixed XYZZ additions (8M + 2S each), prefetching the next
+//              affine point (two 128-bit loads per coordinate) while it adds the current one.  Work
+//              per thread is bounded whatever the scalar distribution (witness columns are far from
+//              uniform: zeros, bits, small limbs).
+//   combine    kCombineLanes lanes per bucket fold the bucket's slice sums (warp shuffles).
+//   reduce     sum_b b * B_b  =  sum_j 2^j * S_j  with  S_j = sum of buckets whose index has bit j set:
+//              c independent tree sums, fully parallel; the final 2c-step Horner runs on the host
+//              in microseconds instead of as a latency-bound single-thread chain on the device.
+//
+// The kernels are integer-ALU bound: 96 algorithmic bytes per point against ~10 field products per
+// window per point.  DESIGN.md carries the roofline arithmetic.
+#include "common.cuh"
+
+namespace zkw {
+
+constexpr int kSlice = 32;         // entries per accumulate thread
+constexpr int kCombineLanes = 8;   // lanes per bucket in the combine kernel
+constexpr int kReduceBlocks = 16;  // CTAs per (group, bit) in the bit-sliced reduction
+constexpr int kReduceThreads = 128;
+
+struct MsmPlan {
+    int c;            // window bits
+    int windows;      // W
+    int groups;       // G: 1 with window tables, W otherwise
+    uint32_t nb;      // buckets per group = 2^(c-1)
+    size_t n;
+    size_t max_entries() const { return (size_t)windows * n; }
+    size_t total_buckets() const { return (size_t)groups * nb; }
+    size_t max_slices() const { return max_entries() / kSlice + total_buckets(); }
+};
+
+// ---- recode + histogram -----------------------------------------------------------------------
+__global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ digits,
+                                  uint32_t* __restrict__ counts, size_t n, int c, int windows, int groups, uint32_t nb) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = Fr::load_nc(scalars + 2 * i).from_mont();
+    uint32_t carry = 0;
+    const uint32_t half = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1u;
+    for (int w = 0; w < windows; w++) {
+        const int bit = w * c;
+        uint32_t v = 0;
+        if (bit < 256) {
+            const int limb = bit >> 5, off = bit & 31;
+            uint64_t two = s.l[limb];
+            if (limb + 1 < 8) two |= (uint64_t)s.l[limb + 1] << 32;
+            v = (uint32_t)(two >> off) & mask;
+        }
+        v += carry;
+        uint32_t out = 0;
+        if (v > half) {  // negative digit: v - 2^c
+            carry = 1;
+            out = 0x80000000u | ((1u << c) - v);
+        } else {
+            carry = 0;
+            out = v;
+        }
+        digits[(size_t)w * n + i] = out;
+        const uint32_t mag = out & 0x7fffffffu;
+        if (mag) atomicAdd(&counts[(groups > 1 ? (size_t)w * nb : 0) + (mag - 1)], 1u);
+    }
+}
+
+// ---- single-CTA exclusive scans: bucket offsets and slice starts ------------------------------
+__global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                                        uint32_t* __restrict__ slice_start, size_t total) {
+    __shared__ uint32_t sh_a[1024], sh_b[1024];
+    const int t = threadIdx.x;
+    const size_t per = (total + 1023) / 1024;
+    const size_t lo = (size_t)t * per, hi = lo + per < total ? lo + per : total;
+    uint32_t sa = 0, sb = 0;
+    for (size_t i = lo; i < hi; i++) { uint32_t cnt = counts[i]; sa += cnt; sb += (cnt + kSlice - 1) / kSlice; }
+    sh_a[t] = sa; sh_b[t] = sb;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t va = 0, vb = 0;
+        if (t >= d) { va = sh_a[t - d]; vb = sh_b[t - d]; }
+        __syncthreads();
+        sh_a[t] += va; sh_b[t] += vb;
+        __syncthreads();
+    }
+    uint32_t ra = sh_a[t] - sa, rb = sh_b[t] - sb;  // exclusive prefix of this thread's run
+    for (size_t i = lo; i < hi; i++) {
+        uint32_t cnt = counts[i];
+        offsets[i] = ra; slice_start[i] = rb;
+        ra += cnt; rb += (cnt + kSlice - 1) / kSlice;
+    }
+    if (t == 1023) { offsets[total] = sh_a[1023]; slice_start[total] = sh_b[1023]; }
+}
+
+// ---- scatter entries into bucket order ----------------------------------------------------------
+__global__ void msm_scatter_kernel(const uint32_t* __restrict__ digits, const uint32_t* __restrict__ offsets,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted, size_t n, int windows,
+                                   int groups, uint32_t nb, int table) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (size_t)windows * n) return;
+    const uint32_t d = digits[e];
+    const uint32_t mag = d & 0x7fffffffu;
+    if (!mag) return;
+    const size_t w = e / n, i = e - w * n;
+    const size_t b = (groups > 1 ? w * nb : 0) + (mag - 1);
+    const uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
+    const uint32_t pidx = table ? (uint32_t)e : (uint32_t)i;  // table[w*n + i] = 2^(c w) P_i
+    sorted[pos] = (d & 0x80000000u) | pidx;
+}
+
+// ---- accumulate: one thread per slice -------------------------------------------------------------
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __restrict__ points, const uint32_t* __restrict__ sorted,
+                                                             const uint32_t* __restrict__ offsets,
+                                                             const uint32_t* __restrict__ slice_start, uint4* __restrict__ partials,
+                                                             uint32_t total_buckets) {
+    const uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nslices = slice_start[total_buckets];
+    if (sl >= nslices) return;
+    // bucket of this slice: last b with slice_start[b] <= sl (empty buckets share a start with the next)
+    uint32_t lo = 0, hi = total_buckets;  // invariant: slice_start[lo] <= sl < slice_start[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (slice_start[mid] <= sl) lo = mid; else hi = mid;
+    }
+    const uint32_t b = lo;
+    const uint32_t begin = offsets[b] + (sl - slice_start[b]) * kSlice;
+    const uint32_t bend = offsets[b + 1];
+    const uint32_t end = begin + kSlice < bend ? begin + kSlice : bend;
+    uint32_t e = sorted[begin];
+    G1Affine cur = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
+    if (e >> 31) cur.y = cur.y.neg();
+    G1Xyzz acc = G1Xyzz::from_affine(cur);
+    if (begin + 1 < end) {
+        e = sorted[begin + 1];
+        cur = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
+        for (uint32_t k = begin + 1; k < end; k++) {
+            const bool neg = e >> 31;
+            G1Affine nxt = cur;
+            if (k + 1 < end) {
+                e = sorted[k + 1];
+                nxt = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
+            }
+            acc.add_mixed(cur, neg);
+            cur = nxt;
+        }
+    }
+    acc.store(partials + 8 * (size_t)sl);
+}
+
+__device__ __forceinline__ G1Xyzz shfl_xor_point(const G1Xyzz& p, int lane_mask, unsigned member_mask) {
+    G1Xyzz r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.x.l[i] = __shfl_xor_sync(member_mask, p.x.l[i], lane_mask);
+        r.y.l[i] = __shfl_xor_sync(member_mask, p.y.l[i], lane_mask);
+        r.zz.l[i] = __shfl_xor_sync(member_mask, p.zz.l[i], lane_mask);
+        r.zzz.l[i] = __shfl_xor_sync(member_mask, p.zzz.l[i], lane_mask);
+    }
+    return r;
+}
+
+// ---- combine: kCombineLanes lanes fold one bucket's slice sums --------------------------------------
+__global__ void __launch_bounds__(128) msm_combine_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ slice_start,
+                                                          uint4* __restrict__ buckets, uint32_t total_buckets) {
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t b = gt / kCombineLanes;
+    const int lane = gt % kCombineLanes;
+    G1Xyzz acc = G1Xyzz::identity();
+    if (b < total_buckets) {
+        const uint32_t s0 = slice_start[b], s1 = slice_start[b + 1];
+        for (uint32_t s = s0 + lane; s < s1; s += kCombineLanes) {
+            G1Xyzz p = G1Xyzz::load(partials + 8 * (size_t)s);
+            acc.add(p);
+        }
+    }
+#pragma unroll
+    for (int m = kCombineLanes / 2; m >= 1; m >>= 1) {
+        G1Xyzz o = shfl_xor_point(acc, m, 0xffffffffu);
+        acc.add(o);
+    }
+    if (b < total_buckets && lane == 0) acc.store(buckets + 8 * (size_t)b);
+}
+
+// ---- bit-sliced reduction: S[g][j] = sum over buckets of group g whose (index+1) has bit j ------------
+__global__ void __launch_bounds__(kReduceThreads) msm_bitreduce_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ block_out,
+                                                                       uint32_t nb, int c) {
+    __shared__ uint4 sh[(kReduceThreads / 32) * 8];
+    const int j = blockIdx.y, g = blockIdx.z;
+    const uint4* grp = buckets + 8 * (size_t)g * nb;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t b = blockIdx.x * kReduceThreads + threadIdx.x; b < nb; b += kReduceBlocks * kReduceThreads) {
+        if (((b + 1) >> j) & 1u) {
+            G1Xyzz p = G1Xyzz::load(grp + 8 * (size_t)b);
+            acc.add(p);
+        }
+    }
+    // warp tree, then one partial per warp through shared memory
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        G1Xyzz o = shfl_xor_point(acc, m, 0xffffffffu);
+        acc.add(o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) acc.store(sh + 8 * warp);
+    __syncthreads();
+    if (warp == 0) {
+        G1Xyzz v = lane < kReduceThreads / 32 ? G1Xyzz::load(sh + 8 * lane) : G1Xyzz::identity();
+#pragma unroll
+        for (int m = kReduceThreads / 64; m >= 1; m >>= 1) {
+            G1Xyzz o = shfl_xor_point(v, m, 0xffffffffu);
+            v.add(o);
+        }
+        if (lane == 0) v.store(block_out + 8 * ((size_t)(g * c + j) * kReduceBlocks + blockIdx.x));
+    }
+}
+
+// one warp per (g, j): fold the kReduceBlocks partials
+__global__ void __launch_bounds__(32) msm_bitreduce_final_kernel(const uint4* __restrict__ block_out, uint4* __restrict__ out) {
+    const int lane = threadIdx.x;
+    const size_t gj = blockIdx.x;
+    G1Xyzz v = lane < kReduceBlocks ? G1Xyzz::load(block_out + 8 * (gj * kReduceBlocks + lane)) : G1Xyzz::identity();
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        G1Xyzz o = shfl_xor_point(v, m, 0xffffffffu);
+        v.add(o);
+    }
+    if (lane == 0) v.store(out + 8 * gj);
+}
+
+// ---- window tables for a resident basis: table[w*n + i] = 2^(c w) P_i ----------------------------------
+// One thread per point: doubles in XYZZ, then normalises its W-1 multiples with one shared inversion.
+template <int MAXW>
+__global__ void __launch_bounds__(128) msm_table_kernel(const uint4* __restrict__ points, uint4* __restrict__ table, size_t n, int c,
+                                                        int windows) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    G1Affine p = G1Affine::load_nc(points + 4 * i);
+    p.store(table + 4 * i);
+    if (p.is_identity()) {
+        for (int w = 1; w < windows; w++) p.store(table + 4 * ((size_t)w * n + i));
+        return;
+    }
+    G1Xyzz cur = G1Xyzz::from_affine(p);
+    Fq xs[MAXW], ys[MAXW], zz[MAXW], zzz[MAXW], pref[MAXW];
+    Fq run = Fq::one();
+    for (int w = 1; w < windows; w++) {
+        for (int d = 0; d < c; d++) cur = cur.dbl();
+        xs[w] = cur.x; ys[w] = cur.y; zz[w] = cur.zz; zzz[w] = cur.zzz;
+        pref[w] = run;                      // product of t_1..t_{w-1}, t = zz*zzz
+        run = run * (cur.zz * cur.zzz);
+    }
+    Fq inv = run.inv();
+    for (int w = windows - 1; w >= 1; w--) {
+        Fq tinv = inv * pref[w];            // 1/(zz_w * zzz_w)
+        inv = inv * (zz[w] * zzz[w]);
+        G1Affine q;
+        q.x = xs[w] * (zzz[w] * tinv);      // X / ZZ
+        q.y = ys[w] * (zz[w] * tinv);       // Y / ZZZ
+        q.store(table + 4 * ((size_t)w * n + i));
+    }
+}
+
+// ---- Jacobian -> affine, one thread per point (C::Curve::batch_normalize; small m) ---------------------
+__global__ void g1_normalize_kernel(const uint4* __restrict__ xyz, uint4* __restrict__ xy, size_t m) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    Fq x = Fq::load(xyz + 6 * i), y = Fq::load(xyz + 6 * i + 2), z = Fq::load(xyz + 6 * i + 4);
+    G1Affine a;
+    if (z.is_zero()) { a.x = Fq::zero(); a.y = Fq::zero(); }
+    else {
+        Fq zi = z.inv(), zi2 = zi.sqr();
+        a.x = x * zi2;
+        a.y = y * (zi2 * zi);
+    }
+    a.store(xy + 4 * i);
+}
+
+int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev) {
+    if (m == 0) return ZKW_OK;
+    g1_normalize_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>((const uint4*)xyz_dev, (uint4*)out_xy_dev, m);
+    ZKW_LAUNCHED(ctx);
+    return ZKW_OK;
+}
+
+static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
+    if (ctx->msm_window_bits > 0) return ctx->msm_window_bits;
+    return n >= (1u << 13) ? 16 : 8;
+}
+
+static void make_plan(MsmPlan& p, size_t n, int c, bool table) {
+    p.c = c;
+    p.windows = (255 + c - 1) / c;
+    p.groups = table ? 1 : p.windows;
+    p.nb = 1u << (c - 1);
+    p.n = n;
+}
+
+void msm_free_basis(MsmBasis& b) {
+    if (b.points) cudaFree(b.points);
+    if (b.table) cudaFree(b.table);
+    b = MsmBasis();
+}
+
+int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b) {
+    if (!ctx->msm_precompute || b.n == 0) return ZKW_OK;
+    const int c = pick_window_bits(ctx, b.n);
+    MsmPlan p;
+    make_plan(p, b.n, c, true);
+    if ((size_t)p.windows * b.n >= (1ull << 31)) return ZKW_OK;  // entry ids carry the sign in bit 31
+    if (p.windows > 32) return ZKW_OK;
+    if (b.table) { cudaFree(b.table); b.table = nullptr; }
+    cudaError_t e = cudaMalloc((void**)&b.table, (size_t)p.windows * b.n * 64);
+    if (e != cudaSuccess) { b.table = nullptr; cudaGetLastError(); return ZKW_OK; }  // fall back to per-window groups
+    msm_table_kernel<32><<<(unsigned)((b.n + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)b.points, (uint4*)b.table, b.n, c, p.windows);
+    ZKW_LAUNCHED(ctx);
+    b.c = c;
+    b.windows = p.windows;
+    return ZKW_OK;
+}
+
+// host-side tail: sum_g 2^(c g) sum_j 2^j S[g][j], then affine normalisation
+static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, int c, uint64_t out_xyz[12]) {
+    G1Xyzz acc = G1Xyzz::identity();
+    for (int g = groups - 1; g >= 0; g--) {
+        for (int j = c - 1; j >= 0; j--) {
+            acc = acc.dbl();
+            G1Xyzz s;
+            memcpy(&s, s_xyzz + 32 * ((size_t)g * c + j), 128);
+            acc.add(s);
+        }
+    }
+    Fq x = Fq::zero(), y = Fq::one(), z = Fq::zero();
+    if (!acc.is_identity()) {
+        // x = X/ZZ, y = Y/ZZZ with one inversion of ZZ*ZZZ
+        Fq tinv = (acc.zz * acc.zzz).inv();
+        x = acc.x * (acc.zzz * tinv);
+        y = acc.y * (acc.zz * tinv);
+        z = Fq::one();
+    }
+    memcpy(out_xyz, x.l, 32);
+    memcpy(out_xyz + 4, y.l, 32);
+    memcpy(out_xyz + 8, z.l, 32);
+}
+
+int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
+            uint64_t out_xyz_host[12]) {
+    if (n == 0) {
+        memset(out_xyz_host, 0, 96);
+        Fq one = Fq::one();
+        memcpy(out_xyz_host + 4, one.l, 32);
+        return ZKW_OK;
+    }
+    const uint64_t* points = bases_dev;
+    bool table = false;
+    int c = pick_window_bits(ctx, n);
+    if (which_bases == ZKW_BASES_G || which_bases == ZKW_BASES_G_LAGRANGE) {
+        MsmBasis& b = ctx->bases[which_bases];
+        if (!b.points) return ZKW_ERR_STATE;
+        if (n > b.n) return ZKW_ERR_INVALID;
+        if (b.table && n == b.n) { points = b.table; table = true; c = b.c; }
+        else points = b.points;
+    } else if (which_bases != ZKW_BASES_CALLER || !bases_dev) {
+        return ZKW_ERR_INVALID;
+    }
+    MsmPlan p;
+    make_plan(p, n, c, table);
+    if (p.max_entries() >= (1ull << 31)) return ZKW_ERR_INVALID;
+    const size_t tb = p.total_buckets();
+    const size_t max_slices = p.max_slices();
+    // workspace layout
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_digits = take(p.max_entries() * 4);
+    const size_t o_sorted = take(p.max_entries() * 4);
+    const size_t o_counts = take(tb * 4);
+    const size_t o_cursor = take(tb * 4);
+    const size_t o_offsets = take((tb + 1) * 4);
+    const size_t o_slices = take((tb + 1) * 4);
+    const size_t o_partials = take(max_slices * 128);
+    const size_t o_buckets = take(tb * 128);
+    const size_t o_blocks = take((size_t)p.groups * c * kReduceBlocks * 128);
+    const size_t o_out = take((size_t)p.groups * c * 128);
+    ZKW_TRY(ensure_buffer(ctx, ctx->msm_ws, off));
+    char* ws = (char*)ctx->msm_ws.ptr;
+    uint32_t* digits = (uint32_t*)(ws + o_digits);
+    uint32_t* sorted = (uint32_t*)(ws + o_sorted);
+    uint32_t* counts = (uint32_t*)(ws + o_counts);
+    uint32_t* cursor = (uint32_t*)(ws + o_cursor);
+    uint32_t* offsets = (uint32_t*)(ws + o_offsets);
+    uint32_t* slices = (uint32_t*)(ws + o_slices);
+    uint4* partials = (uint4*)(ws + o_partials);
+    uint4* buckets = (uint4*)(ws + o_buckets);
+    uint4* blocks = (uint4*)(ws + o_blocks);
+    uint4* outs = (uint4*)(ws + o_out);
+    cudaStream_t st = ctx->stream;
+    // counts and cursor are adjacent: one memset
+    ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
+    msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb);
+    ZKW_LAUNCHED(ctx);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, tb);
+    ZKW_LAUNCHED(ctx);
+    msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0);
+    ZKW_LAUNCHED(ctx);
+    msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb);
+    ZKW_LAUNCHED(ctx);
+    msm_combine_kernel<<<(unsigned)((tb * kCombineLanes + 127) / 128), 128, 0, st>>>(partials, slices, buckets, (uint32_t)tb);
+    ZKW_LAUNCHED(ctx);
+    msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c);
+    ZKW_LAUNCHED(ctx);
+    msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs);
+    ZKW_LAUNCHED(ctx);
+    const size_t out_bytes = (size_t)p.groups * c * 128;
+    if (ctx->pinned_bytes < out_bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned = nullptr;
+        ctx->pinned_bytes = 0;
+        ZKW_CUDA(ctx, cudaMallocHost(&ctx->pinned, out_bytes));
+        ctx->pinned_bytes = out_bytes;
+    }
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, outs, out_bytes, cudaMemcpyDeviceToHost, st));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+    msm_host_tail((const uint32_t*)ctx->pinned, p.groups, c, out_xyz_host);
+    return ZKW_OK;
+}
+
+}  // namespace zkw

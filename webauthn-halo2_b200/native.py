@@ -1,0 +1,335 @@
+"""ctypes binding of libzkw_b200.so — the C ABI of include/zkw_b200.h.
+
+This is the host-side mirror of the seam a patched halo2_proofs would bind over Rust FFI (see
+INTEGRATION.md): `Context.msm` <-> best_multiexp, `Context.ntt` <-> best_fft,
+`lagrange_to_coeff / coeff_to_extended / extended_to_coeff` <-> the EvaluationDomain methods,
+`Context.quotient` <-> evaluate_h + divide_by_vanishing_poly.  The reference reaches those through
+create_proof / keygen at halo2-circuits/src/ecc/ecdsa_p256.rs:259-260, 366-373, 416-423, 555-562.
+
+There is no CPU fallback: a missing library raises at import of the symbol table, and a missing
+GPU raises ZkwError(ZKW_ERR_NO_DEVICE) from Context().
+
+Array convention (numpy uint64, C-contiguous): Fr/Fq vectors (n, 4); affine points (n, 8);
+Jacobian points (12,) — all in halo2curves' Montgomery in-memory form.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libzkw_b200.so")
+
+ZKW_OK = 0
+ZKW_ERR_NO_DEVICE = -1
+ZKW_ERR_CUDA = -2
+ZKW_ERR_INVALID = -3
+ZKW_ERR_OOM = -4
+ZKW_ERR_STATE = -5
+ZKW_ERR_UNSUPPORTED = -6
+
+BASES_G, BASES_G_LAGRANGE, BASES_CALLER = 0, 1, 2
+
+u64p = C.POINTER(C.c_uint64)
+
+# every symbol include/zkw_b200.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTS = [
+    "zkw_ctx_create", "zkw_ctx_destroy", "zkw_ctx_sync", "zkw_ctx_stream", "zkw_strerror", "zkw_last_cuda_error",
+    "zkw_ctx_launch_count", "zkw_srs_load", "zkw_srs_load_dev", "zkw_msm_config", "zkw_msm_bn254_g1",
+    "zkw_msm_bn254_g1_dev", "zkw_msm_bn254_g1_dev_to_host", "zkw_g1_batch_normalize", "zkw_ntt_bn254_fr",
+    "zkw_ntt_bn254_fr_dev", "zkw_lagrange_to_coeff", "zkw_lagrange_to_coeff_dev", "zkw_coeff_to_lagrange",
+    "zkw_coeff_to_lagrange_dev", "zkw_coeff_to_extended", "zkw_coeff_to_extended_dev", "zkw_extended_to_coeff",
+    "zkw_extended_to_coeff_dev", "zkw_quotient_ecdsa", "zkw_quotient_ecdsa_dev", "zkw_dev_alloc", "zkw_dev_free",
+    "zkw_memcpy_h2d", "zkw_memcpy_d2h",
+]
+
+
+class ZkwError(RuntimeError):
+    def __init__(self, status: int, what: str, detail: str = ""):
+        self.status = status
+        super().__init__(f"{what}: status {status} ({_strerror(status)}){' — ' + detail if detail else ''}")
+
+
+class CircuitShape(C.Structure):
+    """zkw_circuit_shape: what ECDSACircuit::configure (ecdsa_p256.rs:94-115) yields for a config line."""
+    _fields_ = [(n, C.c_uint32) for n in
+                ("k", "ext_k", "num_advice", "num_lookup_advice", "num_fixed", "blinding_factors", "cs_degree", "reserved")]
+
+    @classmethod
+    def from_config(cls, degree: int, num_advice: int, num_lookup_advice: int, num_fixed: int = 1,
+                    blinding_factors: int = 6) -> "CircuitShape":
+        # halo2-lib's RangeConfig folds the lookup into the single gate column behind a q_lookup
+        # selector when num_advice == 1 (lookup input q*a has degree 2 => cs degree 5)
+        selector_mode = num_advice == 1
+        lookup_cols = 0 if selector_mode else num_lookup_advice
+        deg = 5 if selector_mode else 4
+        ek = degree
+        while (1 << ek) < (1 << degree) * (deg - 1):
+            ek += 1
+        return cls(degree, ek, num_advice, lookup_cols, num_fixed, blinding_factors, deg, 0)
+
+    @property
+    def perm_columns(self) -> int:
+        return self.num_fixed + self.num_advice + self.num_lookup_advice
+
+    @property
+    def perm_sets(self) -> int:
+        chunk = self.cs_degree - 2
+        return (self.perm_columns + chunk - 1) // chunk
+
+    @property
+    def lookups(self) -> int:
+        return self.num_lookup_advice or 1
+
+
+class QuotientInputs(C.Structure):
+    _fields_ = [
+        ("shape", CircuitShape),
+        ("advice", C.POINTER(u64p)), ("constants", C.POINTER(u64p)), ("table", u64p),
+        ("q_enable", C.POINTER(u64p)), ("q_lookup", u64p), ("sigma", C.POINTER(u64p)),
+        ("perm_z", C.POINTER(u64p)), ("lookup_z", C.POINTER(u64p)), ("lookup_a", C.POINTER(u64p)),
+        ("lookup_s", C.POINTER(u64p)), ("l0", u64p), ("l_last", u64p), ("l_active", u64p),
+        ("y", C.c_uint64 * 4), ("beta", C.c_uint64 * 4), ("gamma", C.c_uint64 * 4), ("theta", C.c_uint64 * 4),
+    ]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load libzkw_b200.so; raise (never fall back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). The B200 path has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.zkw_strerror.restype = C.c_char_p
+    lib.zkw_last_cuda_error.restype = C.c_char_p
+    lib.zkw_last_cuda_error.argtypes = [C.c_void_p]
+    lib.zkw_ctx_stream.restype = C.c_void_p
+    lib.zkw_ctx_stream.argtypes = [C.c_void_p]
+    lib.zkw_ctx_launch_count.restype = C.c_uint64
+    lib.zkw_ctx_launch_count.argtypes = [C.c_void_p]
+    lib.zkw_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.zkw_ctx_destroy.argtypes = [C.c_void_p]
+    lib.zkw_ctx_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _strerror(status: int) -> str:
+    try:
+        return load_library().zkw_strerror(status).decode()
+    except Exception:  # pragma: no cover
+        return "?"
+
+
+def _as_u64(a: np.ndarray, cols: int | None = None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(u64p)
+
+
+def _addr(x) -> C.c_void_p:
+    """device address from an int, a ctypes pointer, or anything with .data_ptr() (torch tensors)."""
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    return C.cast(x, C.c_void_p)
+
+
+class Context:
+    """One zkw_ctx: bound to one CUDA device, one stream.  One Context per GPU / per process."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.zkw_ctx_create(device, C.byref(h))
+        if rc != ZKW_OK:
+            raise ZkwError(rc, "zkw_ctx_create")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.zkw_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != ZKW_OK:
+            detail = (self.lib.zkw_last_cuda_error(self.h) or b"").decode() if rc in (ZKW_ERR_CUDA, ZKW_ERR_OOM) else ""
+            raise ZkwError(rc, what, detail)
+
+    # -- plumbing ---------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return int(self.lib.zkw_ctx_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.zkw_ctx_launch_count(self.h))
+
+    def sync(self):
+        self._check(self.lib.zkw_ctx_sync(self.h), "zkw_ctx_sync")
+
+    def msm_config(self, window_bits: int = 0, precompute: bool = True):
+        self._check(self.lib.zkw_msm_config(self.h, window_bits, int(precompute)), "zkw_msm_config")
+
+    # -- SRS ----------------------------------------------------------------------------------
+    def srs_load(self, g: np.ndarray, g_lagrange: np.ndarray | None = None):
+        g = _as_u64(g, 8)
+        gl = _as_u64(g_lagrange, 8) if g_lagrange is not None else None
+        if gl is not None and gl.shape != g.shape:
+            raise ValueError("g and g_lagrange must have the same length")
+        self._check(self.lib.zkw_srs_load(self.h, _p(g), _p(gl) if gl is not None else None, C.c_size_t(g.shape[0])), "zkw_srs_load")
+
+    def srs_load_dev(self, g_dev, g_lagrange_dev, n: int):
+        self._check(self.lib.zkw_srs_load_dev(self.h, _addr(g_dev), _addr(g_lagrange_dev) if g_lagrange_dev is not None else None,
+                                              C.c_size_t(n)), "zkw_srs_load_dev")
+
+    # -- MSM: best_multiexp ---------------------------------------------------------------------
+    def msm(self, scalars: np.ndarray, bases: np.ndarray | None = None, which: int | None = None) -> np.ndarray:
+        """sum_i scalars[i] * bases[i] -> Jacobian (12,) with Z = 1 (or Z = 0 for the identity)."""
+        s = _as_u64(scalars, 4)
+        if which is None:
+            which = BASES_CALLER if bases is not None else BASES_G
+        out = np.zeros(12, dtype=np.uint64)
+        if which == BASES_CALLER:
+            b = _as_u64(bases, 8)
+            if b.shape[0] != s.shape[0]:
+                raise ValueError("scalars / bases length mismatch")
+            rc = self.lib.zkw_msm_bn254_g1(self.h, which, _p(b), _p(s), C.c_size_t(s.shape[0]), _p(out))
+        else:
+            rc = self.lib.zkw_msm_bn254_g1(self.h, which, None, _p(s), C.c_size_t(s.shape[0]), _p(out))
+        self._check(rc, "zkw_msm_bn254_g1")
+        return out
+
+    def msm_dev(self, scalars_dev, n: int, which: int = BASES_G, bases_dev=None) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        rc = self.lib.zkw_msm_bn254_g1_dev_to_host(self.h, which, _addr(bases_dev) if bases_dev is not None else None,
+                                                   _addr(scalars_dev), C.c_size_t(n), _p(out))
+        self._check(rc, "zkw_msm_bn254_g1_dev_to_host")
+        return out
+
+    def g1_batch_normalize(self, xyz: np.ndarray) -> np.ndarray:
+        x = _as_u64(xyz, 12)
+        out = np.zeros((x.shape[0], 8), dtype=np.uint64)
+        self._check(self.lib.zkw_g1_batch_normalize(self.h, _p(x), C.c_size_t(x.shape[0]), _p(out)), "zkw_g1_batch_normalize")
+        return out
+
+    # -- NTT: best_fft and the EvaluationDomain transforms ------------------------------------------
+    def ntt(self, a: np.ndarray, omega: np.ndarray, scale: np.ndarray | None = None) -> np.ndarray:
+        a = np.array(_as_u64(a, 4), copy=True)
+        n = a.shape[0]
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise ZkwError(ZKW_ERR_INVALID, "ntt", "length must be a power of two")
+        om = _as_u64(omega).reshape(4)
+        sc = _as_u64(scale).reshape(4) if scale is not None else None
+        self._check(self.lib.zkw_ntt_bn254_fr(self.h, _p(a), C.c_uint(log_n), _p(om), _p(sc) if sc is not None else None), "zkw_ntt_bn254_fr")
+        return a
+
+    def ntt_dev(self, a_dev, log_n: int, omega: np.ndarray, scale: np.ndarray | None = None):
+        om = _as_u64(omega).reshape(4)
+        sc = _as_u64(scale).reshape(4) if scale is not None else None
+        self._check(self.lib.zkw_ntt_bn254_fr_dev(self.h, _addr(a_dev), C.c_uint(log_n), _p(om), _p(sc) if sc is not None else None),
+                    "zkw_ntt_bn254_fr_dev")
+
+    def lagrange_to_coeff(self, a: np.ndarray) -> np.ndarray:
+        a = np.array(_as_u64(a, 4), copy=True)
+        k = a.shape[0].bit_length() - 1
+        self._check(self.lib.zkw_lagrange_to_coeff(self.h, _p(a), C.c_uint(k)), "zkw_lagrange_to_coeff")
+        return a
+
+    def coeff_to_lagrange(self, a: np.ndarray) -> np.ndarray:
+        a = np.array(_as_u64(a, 4), copy=True)
+        k = a.shape[0].bit_length() - 1
+        self._check(self.lib.zkw_coeff_to_lagrange(self.h, _p(a), C.c_uint(k)), "zkw_coeff_to_lagrange")
+        return a
+
+    def coeff_to_extended(self, a: np.ndarray, ext_k: int) -> np.ndarray:
+        a = _as_u64(a, 4)
+        k = a.shape[0].bit_length() - 1
+        out = np.zeros((1 << ext_k, 4), dtype=np.uint64)
+        self._check(self.lib.zkw_coeff_to_extended(self.h, _p(a), C.c_uint(k), C.c_uint(ext_k), _p(out)), "zkw_coeff_to_extended")
+        return out
+
+    def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
+        a = np.array(_as_u64(a, 4), copy=True)
+        ek = a.shape[0].bit_length() - 1
+        self._check(self.lib.zkw_extended_to_coeff(self.h, _p(a), C.c_uint(ek)), "zkw_extended_to_coeff")
+        return a
+
+    def lagrange_to_coeff_dev(self, a_dev, k: int):
+        self._check(self.lib.zkw_lagrange_to_coeff_dev(self.h, _addr(a_dev), C.c_uint(k)), "zkw_lagrange_to_coeff_dev")
+
+    def coeff_to_lagrange_dev(self, a_dev, k: int):
+        self._check(self.lib.zkw_coeff_to_lagrange_dev(self.h, _addr(a_dev), C.c_uint(k)), "zkw_coeff_to_lagrange_dev")
+
+    def coeff_to_extended_dev(self, coeffs_dev, k: int, ext_k: int, out_dev):
+        self._check(self.lib.zkw_coeff_to_extended_dev(self.h, _addr(coeffs_dev), C.c_uint(k), C.c_uint(ext_k), _addr(out_dev)),
+                    "zkw_coeff_to_extended_dev")
+
+    def extended_to_coeff_dev(self, a_dev, ext_k: int):
+        self._check(self.lib.zkw_extended_to_coeff_dev(self.h, _addr(a_dev), C.c_uint(ext_k)), "zkw_extended_to_coeff_dev")
+
+    # -- quotient: evaluate_h + divide_by_vanishing_poly --------------------------------------------
+    @staticmethod
+    def _quotient_struct(shape: CircuitShape, cols: dict, challenges: dict, ptr_of):
+        keep = []
+
+        def table(name):
+            lst = cols.get(name) or []
+            t = (u64p * max(len(lst), 1))()
+            for i, a in enumerate(lst):
+                t[i] = ptr_of(a)
+            keep.append(t)
+            return C.cast(t, C.POINTER(u64p))
+
+        def single(name):
+            a = cols.get(name)
+            return ptr_of(a) if a is not None else C.cast(None, u64p)
+
+        q = QuotientInputs()
+        q.shape = shape
+        for name in ("advice", "constants", "q_enable", "sigma", "perm_z", "lookup_z", "lookup_a", "lookup_s"):
+            setattr(q, name, table(name))
+        for name in ("table", "q_lookup", "l0", "l_last", "l_active"):
+            setattr(q, name, single(name))
+        for name in ("y", "beta", "gamma", "theta"):
+            v = np.asarray(challenges[name], dtype=np.uint64).reshape(4)
+            getattr(q, name)[:] = [int(x) for x in v]
+        return q, keep
+
+    def quotient(self, shape: CircuitShape, cols: dict, challenges: dict) -> np.ndarray:
+        """cols: name -> (2^ext_k, 4) array, or list of them for advice / constants / q_enable / sigma /
+        perm_z / lookup_z / lookup_a / lookup_s.  Returns h on the extended coset."""
+        cols = {k: ([_as_u64(x, 4) for x in v] if isinstance(v, (list, tuple)) else (_as_u64(v, 4) if v is not None else None))
+                for k, v in cols.items()}
+        q, keep = self._quotient_struct(shape, cols, challenges, _p)
+        out = np.zeros((1 << shape.ext_k, 4), dtype=np.uint64)
+        self._check(self.lib.zkw_quotient_ecdsa(self.h, C.byref(q), _p(out)), "zkw_quotient_ecdsa")
+        del keep
+        return out
+
+    def quotient_dev(self, shape: CircuitShape, cols_dev: dict, challenges: dict, h_dev):
+        q, keep = self._quotient_struct(shape, cols_dev, challenges, lambda a: C.cast(_addr(a), u64p))
+        self._check(self.lib.zkw_quotient_ecdsa_dev(self.h, C.byref(q), _addr(h_dev)), "zkw_quotient_ecdsa_dev")
+        del keep
