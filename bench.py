@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py — proofs/s for the P-256 ECDSA circuit's prover hot path at k = 19 on N B200s.
+
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line from rank 0.  A "step" is one pass of the hot path for ONE proof at the k = 19 shape of
+halo2-circuits/src/configs/bench_ecdsa.config:1 (1 advice / 1 lookup / 1 fixed column; degree-5
+constraint system, extended domain 2^21) with the EVM-transcript (GWC) opening count of
+BASELINE.json configs[1]:
+
+    15 MSMs of 2^19 points   (advice, A', S', Z_perm, Z_lookup over g_lagrange; random poly,
+                              4 quotient pieces, 5 GWC witnesses over g)
+     5 iNTT(2^19)            lagrange_to_coeff of advice, A', S', Z_perm, Z_lookup
+     5 NTT(2^19 -> 2^21)     coeff_to_extended of the same
+     1 quotient evaluation   2^21 rows, 14 input cosets
+     1 iNTT(2^21)            extended_to_coeff of h
+
+on synthetic uniformly random columns (the worst case for the MSM: every window of every scalar
+is populated).  `value` times this with all inputs resident in HBM; `e2e` times the same sequence
+through the host-pointer C ABI (what a drop-in FFI call from halo2_proofs pays), host<->device
+copies included.  `--impl reference` times the CPU oracle (a restatement of the upstream CPU
+algorithms; the Rust prover cannot be built here) on the host cores.
+
+One process per GPU; independent proofs shard with no collective (torch.distributed is used only
+for the barrier and the max-over-ranks of the elapsed time).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K = 19
+METRIC = "P-256 ECDSA proofs/sec at k=19"
+UNIT = "proofs/s"
+N_MSM_LAGRANGE, N_MSM_G = 5, 10
+N_INTT, N_EXT, N_IEXT, N_QUOT = 5, 5, 1, 1
+WORKLOAD = ("ECDSA circuit k=19 (1 advice/1 lookup/1 fixed, ext 2^21), prover hot path per proof: "
+            "15 MSM(2^19) + 5 iNTT(2^19) + 5 cosetNTT(2^19->2^21) + quotient(2^21 rows) + 1 iNTT(2^21), GWC opening count")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.device)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+class HotPathProof:
+    """Device-resident state for one prover: SRS + proving-key cosets (fixed per circuit) and one
+    proof's worth of synthetic witness-derived columns."""
+
+    def __init__(self, zkw, ctx, torch, k: int, seed: int):
+        self.zkw, self.ctx, self.torch, self.k = zkw, ctx, torch, k
+        self.shape = zkw.CircuitShape.from_config(k, 1, 1, 1)
+        self.ek = self.shape.ext_k
+        self.n, self.en = 1 << k, 1 << self.ek
+        dev = torch.device("cuda", ctx.device)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        self.gen = g
+        self.dev = dev
+        # dev SRS (gen_srs analogue) — tau is a fixed development value
+        tau = np.array([0x1234567890ABCDEF, 0x0FEDCBA987654321, 0x1111111111111111, 0x0222222222222222], dtype=np.uint64)
+        ctx.srs_setup(k, tau)
+        # proving-key cosets: constants, table, q_enable, q_lookup, 2 sigma, l0, l_last, l_active
+        self.pk = {name: self.rand_fr(self.en) for name in
+                   ("constants", "table", "q_enable", "q_lookup", "sigma0", "sigma1", "l0", "l_last", "l_active")}
+        self.challenges = {c: self.rand_fr(1).cpu().numpy().view(np.uint64).reshape(4) for c in ("y", "beta", "gamma", "theta")}
+        # per-proof columns (Lagrange basis): advice, A', S', Z_perm, Z_lookup; coefficient form: random poly, 5 GWC witnesses
+        self.lagrange = [self.rand_fr(self.n) for _ in range(5)]
+        self.coeff_polys = [self.rand_fr(self.n) for _ in range(6)]
+        self.work = [torch.empty((self.n, 4), dtype=torch.int64, device=dev) for _ in range(5)]
+        self.ext = [torch.empty((self.en, 4), dtype=torch.int64, device=dev) for _ in range(5)]
+        self.h = torch.empty((self.en, 4), dtype=torch.int64, device=dev)
+        self.commitments = []
+
+    def rand_fr(self, n: int):
+        """uniform field elements < 2^253 (valid Montgomery residues: any value < r is one)"""
+        t = self.torch.randint(0, 1 << 62, (n, 4), dtype=self.torch.int64, device=self.dev, generator=self.gen)
+        t[:, 3] &= (1 << 60) - 1
+        return t
+
+    def input_bytes(self) -> int:
+        return (len(self.lagrange) + len(self.coeff_polys)) * self.n * 32
+
+    def step(self):
+        z, ctx, n, k, ek = self.zkw, self.ctx, self.n, self.k, self.ek
+        out = []
+        # commitments to the Lagrange-basis columns
+        for col in self.lagrange:
+            out.append(ctx.msm_dev(col, n, z.BASES_G_LAGRANGE))
+        out.append(ctx.msm_dev(self.coeff_polys[0], n, z.BASES_G))  # random polynomial
+        # to coefficient form, then onto the extended coset
+        for col, w, e in zip(self.lagrange, self.work, self.ext):
+            w.copy_(col)
+            ctx.lagrange_to_coeff_dev(w, k)
+            ctx.coeff_to_extended_dev(w, k, ek, e)
+        cols = {"advice": [self.ext[0]], "constants": [self.pk["constants"]], "table": self.pk["table"],
+                "q_enable": [self.pk["q_enable"]], "q_lookup": self.pk["q_lookup"],
+                "sigma": [self.pk["sigma0"], self.pk["sigma1"]], "perm_z": [self.ext[3]],
+                "lookup_z": [self.ext[4]], "lookup_a": [self.ext[1]], "lookup_s": [self.ext[2]],
+                "l0": self.pk["l0"], "l_last": self.pk["l_last"], "l_active": self.pk["l_active"]}
+        ctx.quotient_dev(self.shape, cols, self.challenges, self.h)
+        ctx.extended_to_coeff_dev(self.h, ek)
+        # h pieces (4 x n coefficients) and the GWC witness polynomials
+        for i in range(4):
+            out.append(ctx.msm_dev(self.h[i * n:(i + 1) * n], n, z.BASES_G))
+        for p in self.coeff_polys[1:]:
+            out.append(ctx.msm_dev(p, n, z.BASES_G))
+        self.commitments = out
+        return out
+
+
+class HostAbiProof:
+    """The same sequence through the host-pointer C ABI (pinned host buffers): what a drop-in FFI
+    call from halo2_proofs pays per best_multiexp / best_fft / evaluate_h call."""
+
+    def __init__(self, zkw, ctx, torch, dev_state: HotPathProof):
+        self.zkw, self.ctx, self.s = zkw, ctx, dev_state
+
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h.numpy().view(np.uint64)
+
+        self.lagrange = [pinned(t) for t in dev_state.lagrange]
+        self.coeff_polys = [pinned(t) for t in dev_state.coeff_polys]
+        self.pk = {k: pinned(v) for k, v in dev_state.pk.items()}
+        self.h2d = 0
+        self.d2h = 0
+
+    def step(self):
+        z, ctx, s = self.zkw, self.ctx, self.s
+        n, k, ek, en = s.n, s.k, s.ek, s.en
+        h2d = d2h = 0
+        out = []
+        for col in self.lagrange:
+            out.append(ctx.msm(col, which=z.BASES_G_LAGRANGE)); h2d += n * 32; d2h += 96
+        out.append(ctx.msm(self.coeff_polys[0], which=z.BASES_G)); h2d += n * 32; d2h += 96
+        ext = []
+        for col in self.lagrange:
+            c = ctx.lagrange_to_coeff(col); h2d += n * 32; d2h += n * 32
+            ext.append(ctx.coeff_to_extended(c, ek)); h2d += n * 32; d2h += en * 32
+        cols = {"advice": [ext[0]], "constants": [self.pk["constants"]], "table": self.pk["table"],
+                "q_enable": [self.pk["q_enable"]], "q_lookup": self.pk["q_lookup"],
+                "sigma": [self.pk["sigma0"], self.pk["sigma1"]], "perm_z": [ext[3]],
+                "lookup_z": [ext[4]], "lookup_a": [ext[1]], "lookup_s": [ext[2]],
+                "l0": self.pk["l0"], "l_last": self.pk["l_last"], "l_active": self.pk["l_active"]}
+        h = ctx.quotient(s.shape, cols, s.challenges); h2d += 14 * en * 32; d2h += en * 32
+        hc = ctx.extended_to_coeff(h); h2d += en * 32; d2h += en * 32
+        for i in range(4):
+            out.append(ctx.msm(hc[i * n:(i + 1) * n], which=z.BASES_G)); h2d += n * 32; d2h += 96
+        for p in self.coeff_polys[1:]:
+            out.append(ctx.msm(p, which=z.BASES_G)); h2d += n * 32; d2h += 96
+        self.h2d, self.d2h = h2d, d2h
+        return out
+
+
+def cpu_hot_path(k: int, threads: int):
+    """Times one of each hot-path call on the CPU oracle and scales by the per-proof counts.
+    Returns (proofs_per_s, sample description, per-call seconds)."""
+    from oracle import cpu
+    n = 1 << k
+    shape = cpu.make_shape(k, 1, 0, 1)
+    ek, en = shape.ext_k, 1 << shape.ext_k
+    dom = cpu.Domain.new(shape.cs_degree, k)
+    t = {}
+    bases = cpu.g1_fixed_base_mul(cpu.fr_random(n, 1), threads)
+    s = cpu.fr_random(n, 2)
+    t0 = time.perf_counter(); cpu.best_multiexp(s, bases, threads); t["msm"] = time.perf_counter() - t0
+    a = cpu.fr_random(n, 3)
+    t0 = time.perf_counter(); c = dom.lagrange_to_coeff(a, threads); t["intt"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); e = dom.coeff_to_extended(c, threads); t["ext"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); dom.extended_to_coeff(e, threads); t["iext"] = time.perf_counter() - t0
+    cols = {"advice": [e], "constants": [e], "table": e, "q_enable": [e], "q_lookup": e, "sigma": [e, e],
+            "perm_z": [e], "lookup_z": [e], "lookup_a": [e], "lookup_s": [e], "l0": e, "l_last": e, "l_active": e}
+    ch = {nme: cpu.fr_random(1, 9)[0] for nme in ("y", "beta", "gamma", "theta")}
+    t0 = time.perf_counter(); cpu.quotient_ecdsa(shape, cols, ch, threads); t["quot"] = time.perf_counter() - t0
+    per_proof = (N_MSM_G + N_MSM_LAGRANGE) * t["msm"] + N_INTT * t["intt"] + N_EXT * t["ext"] + N_IEXT * t["iext"] + N_QUOT * t["quot"]
+    sample = (f"one call each of best_multiexp(2^{k}), lagrange_to_coeff(2^{k}), coeff_to_extended(2^{k}->2^{ek}), "
+              f"extended_to_coeff(2^{ek}), evaluate_h(2^{ek} rows) on {threads} threads, scaled by the per-proof counts 15/5/5/1/1")
+    return 1.0 / per_proof, sample, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu
+    threads = cpu.max_threads()
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample, _ = cpu_hot_path(args.k, threads)
+        if i >= args.warmup:
+            vals.append(v)
+        if i == 0 and args.warmup + args.steps > 2:
+            pass
+    # harmonic mean == total proofs / total time
+    value = len(vals) / sum(1.0 / v for v in vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64x4 Montgomery (254-bit modular integers)", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "k": args.k},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of the upstream algorithms (oracle/); the Rust prover cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    zkw = importlib.import_module("webauthn-halo2_b200")
+    ctx = zkw.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    torch.cuda.set_stream(stream)  # torch-side copies are ordered with the ctx's kernels
+    state = HotPathProof(zkw, ctx, torch, args.k, seed=1234 + rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        state.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.profile_reset()
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        state.step()
+    ev1.record(stream)
+    ev1.synchronize()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    prof = ctx.profile_all()
+    ctx.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * args.steps / (max_ms / 1000.0)
+
+    # end-to-end through the host-pointer C ABI (pinned host buffers, copies inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        host = HostAbiProof(zkw, ctx, torch, state)
+        host.step()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host.step()
+        e1.record(stream)
+        e1.synchronize()
+        wall = time.perf_counter() - t0
+        te = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": host.h2d,
+               "d2h_bytes_per_step": host.d2h, "steps": e2e_steps,
+               "path": "host-pointer C ABI (zkw_msm_bn254_g1 / zkw_lagrange_to_coeff / zkw_coeff_to_extended / zkw_quotient_ecdsa / zkw_extended_to_coeff), pinned host buffers"}
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        n = 1 << args.k
+        acc_ms, acc_cnt = prof.get("msm_accumulate_kernel", (0.0, 0))
+        per_launch_ms = acc_ms / acc_cnt if acc_cnt else None
+        alg_bytes = 96 * n
+        achieved = (alg_bytes / (per_launch_ms / 1000.0) / 1e9) if per_launch_ms else None
+        total_kernel_ms = sum(v[0] for v in prof.values())
+        roofline = {
+            "kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "traffic": None, "peak_source": pk_src + " copy bandwidth (MEASURED_PEAKS.json)",
+            "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms, "launches": acc_cnt,
+            "share_of_kernel_time": (acc_ms / total_kernel_ms) if total_kernel_ms else None,
+            "note": "integer-ALU bound (254-bit Montgomery products), see DESIGN.md; modmul/s beside it",
+            "modmul_per_s": (16 * n * 10 / (per_launch_ms / 1000.0)) if per_launch_ms else None,
+            "modmul_peak_per_s_measured": 68.5e9,
+        }
+        kernels = {name: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for name, v in sorted(prof.items())}
+        cpu_val, cpu_sample, _ = (None, "skipped", None)
+        cores = None
+        if world == 1 and not args.no_cpu:
+            from oracle import cpu as cpu_oracle
+            cores = cpu_oracle.max_threads()
+            cpu_val, cpu_sample, _ = cpu_hot_path(args.k, cores)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 Montgomery (254-bit modular integers)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "k": args.k, "proofs_per_step_per_gpu": 1,
+                       "l2": "working set per step ~1.4 GB (14 cosets x 64 MiB + SRS window tables 2 x 512 MiB) exceeds the 126 MB L2"},
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample},
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--k", type=int, default=K)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

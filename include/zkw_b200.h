@@ -65,10 +65,26 @@ const char* zkw_last_cuda_error(zkw_ctx* ctx);
 /* Number of kernel launches this ctx has issued since creation (bench.py's gpu_launches). */
 uint64_t zkw_ctx_launch_count(zkw_ctx* ctx);
 
+/* Optional per-kernel device timing (CUDA events on the ctx stream), used by bench.py for the
+ * roofline of the dominant kernel.  Kernel names are the __global__ function names
+ * ("msm_accumulate_kernel", "ntt_pass_kernel", "quotient_kernel", ...). */
+int zkw_profile_enable(zkw_ctx* ctx, int on);
+int zkw_profile_reset(zkw_ctx* ctx);
+int zkw_profile_read(zkw_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
+int zkw_profile_names(zkw_ctx* ctx, char* buf, size_t cap); /* comma-separated names seen so far */
+
 /* ---- SRS residency: replaces ParamsKZG{g, g_lagrange} living in host Vec<G1Affine> ------ */
 /* Copies n affine points of each basis to the device once; later MSMs name them by id. */
 int zkw_srs_load(zkw_ctx* ctx, const uint64_t* g /* n*8 */, const uint64_t* g_lagrange /* n*8 or NULL */, size_t n);
 
+/* Development SRS generated on the device for a caller-chosen tau (Montgomery form): the
+ * replacement of halo2-lib's gen_srs(k) / ParamsKZG::setup (ecdsa_p256.rs:258,279,338,388,430):
+ * g[i] = tau^i G and g_lagrange[i] = L_i(tau) G, n = 2^k, both resident (with window tables). */
+int zkw_srs_setup(zkw_ctx* ctx, unsigned k, const uint64_t tau[4]);
+/* Copy the first n points of a resident basis back to the host (n*8 u64). */
+int zkw_srs_get(zkw_ctx* ctx, int which_bases, uint64_t* out_xy, size_t n);
+/* out[i] = scalars[i] * G (G1 generator), affine; host pointers. */
+int zkw_g1_fixed_base_mul(zkw_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out_xy);
 /* Same, from device arrays (the context keeps its own copies). */
 int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagrange_dev, size_t n);
 /* MSM tuning, effective for bases loaded afterwards: window_bits 0 = automatic; precompute != 0 keeps

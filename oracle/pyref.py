@@ -288,3 +288,63 @@ class SplitMix64:
             v |= self.next() << (64 * i)
         v &= (1 << 254) - 1
         return v % mod
+
+
+# --- evaluate_h (+ divide_by_vanishing_poly) for the ECDSA circuit shape, python ints -------------
+def quotient_ecdsa(shape: dict, cols: dict, ch: dict):
+    """Row-by-row restatement of halo2_proofs::plonk::evaluation::Evaluator::evaluate_h followed by
+    divide_by_vanishing_poly for the FlexGate + Range constraint system of ECDSACircuit::configure
+    (halo2-circuits/src/ecc/ecdsa_p256.rs:94-115).  Constraint list and folding order are those of
+    the reference's generated verifier (proving-server/P256Verifier.yul:406-547).
+
+    shape: dict(k, ext_k, num_advice, num_lookup_advice, num_fixed, blinding_factors, cs_degree)
+    cols : canonical ints, lists over the extended domain (same keys as zkw_quotient_inputs)
+    ch   : dict(y, beta, gamma) canonical ints."""
+    k, ek = shape["k"], shape["ext_k"]
+    A, L, F = shape["num_advice"], shape["num_lookup_advice"], shape["num_fixed"]
+    en = 1 << ek
+    rs = 1 << (ek - k)
+    last = -(shape["blinding_factors"] + 1)
+    chunk = shape["cs_degree"] - 2
+    ncols = F + A + L
+    nsets = (ncols + chunk - 1) // chunk
+    nlk = L or 1
+    dom = EvaluationDomain(shape["cs_degree"], k)
+    assert dom.extended_k == ek
+    y, beta, gamma = ch["y"], ch["beta"], ch["gamma"]
+    pcols = list(cols["constants"]) + list(cols["advice"])
+    out = []
+    for i in range(en):
+        rot = lambda r: (i + r * rs) % en
+        v = 0
+        for c in range(A):
+            a = cols["advice"][c]
+            g = cols["q_enable"][c][i] * (a[i] + a[rot(1)] * a[rot(2)] - a[rot(3)])
+            v = (v * y + g) % R
+        l0, ll, la = cols["l0"][i], cols["l_last"][i], cols["l_active"][i]
+        z = cols["perm_z"]
+        v = (v * y + (1 - z[0][i]) * l0) % R
+        v = (v * y + (z[-1][i] * z[-1][i] - z[-1][i]) * ll) % R
+        for s in range(1, nsets):
+            v = (v * y + (z[s][i] - z[s - 1][rot(last)]) * l0) % R
+        x = dom.g_coset * pow(dom.extended_omega, i, R) % R
+        cur = beta * x % R
+        for s in range(nsets):
+            left, right = z[s][rot(1)], z[s][i]
+            for c in range(s * chunk, min((s + 1) * chunk, ncols)):
+                left = left * (pcols[c][i] + beta * cols["sigma"][c][i] + gamma) % R
+                right = right * (pcols[c][i] + cur + gamma) % R
+                cur = cur * FR_DELTA % R
+            v = (v * y + (left - right) * la) % R
+        for q in range(nlk):
+            lz, ap, sp = cols["lookup_z"][q], cols["lookup_a"][q], cols["lookup_s"][q]
+            inp = cols["advice"][A + q][i] if L else cols["q_lookup"][i] * cols["advice"][0][i] % R
+            v = (v * y + (1 - lz[i]) * l0) % R
+            v = (v * y + (lz[i] * lz[i] - lz[i]) * ll) % R
+            lhs = lz[rot(1)] * (ap[i] + beta) % R * (sp[i] + gamma) % R
+            rhs = lz[i] * (inp + beta) % R * (cols["table"][i] + gamma) % R
+            v = (v * y + (lhs - rhs) * la) % R
+            v = (v * y + (ap[i] - sp[i]) * l0) % R
+            v = (v * y + (ap[i] - sp[i]) * (ap[i] - ap[rot(-1)]) % R * la) % R
+        out.append(v * dom.t_evaluations[i % rs] % R)
+    return out

@@ -82,6 +82,48 @@ void domain_consts(unsigned k, unsigned ext_k, DomainConsts* out) {
     *out = d;
 }
 
+// ---- per-kernel timing ---------------------------------------------------------------------------
+static cudaEvent_t take_event(zkw_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
+
+ProfScope::ProfScope(zkw_ctx* c, const char* name) : ctx(c) {
+    if (!c->profiling) return;
+    cudaEvent_t start = take_event(c);
+    stop = take_event(c);
+    if (!start || !stop) { stop = nullptr; return; }
+    cudaEventRecord(start, c->stream);
+    c->prof_pending.push_back({name, start, stop});
+}
+ProfScope::~ProfScope() {
+    if (stop) cudaEventRecord(stop, ctx->stream);
+}
+
+static void profile_collect(zkw_ctx* ctx) {
+    if (ctx->prof_pending.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& r : ctx->prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            auto& t = ctx->prof_totals[r.name];
+            t.first += ms;
+            t.second += 1;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->event_pool.push_back(r.start);
+        ctx->event_pool.push_back(r.stop);
+    }
+    ctx->prof_pending.clear();
+}
+
 static int free_buffer(DeviceBuffer& b) {
     if (b.ptr) cudaFree(b.ptr);
     b.ptr = nullptr;
@@ -160,6 +202,8 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table);
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    profile_collect(ctx);
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -178,6 +222,36 @@ int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute) {
     if (!ctx || window_bits < 0 || window_bits > 20 || window_bits == 1) return ZKW_ERR_INVALID;
     ctx->msm_window_bits = window_bits;
     ctx->msm_precompute = precompute ? 1 : 0;
+    return ZKW_OK;
+}
+
+int zkw_profile_enable(zkw_ctx* ctx, int on) {
+    if (!ctx) return ZKW_ERR_INVALID;
+    profile_collect(ctx);
+    ctx->profiling = on != 0;
+    return ZKW_OK;
+}
+int zkw_profile_reset(zkw_ctx* ctx) {
+    if (!ctx) return ZKW_ERR_INVALID;
+    profile_collect(ctx);
+    ctx->prof_totals.clear();
+    return ZKW_OK;
+}
+int zkw_profile_read(zkw_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches) {
+    if (!ctx || !kernel) return ZKW_ERR_INVALID;
+    profile_collect(ctx);
+    auto it = ctx->prof_totals.find(kernel);
+    if (total_ms) *total_ms = it == ctx->prof_totals.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == ctx->prof_totals.end() ? 0 : it->second.second;
+    return ZKW_OK;
+}
+int zkw_profile_names(zkw_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap == 0) return ZKW_ERR_INVALID;
+    profile_collect(ctx);
+    std::string all;
+    for (auto& kv : ctx->prof_totals) { if (!all.empty()) all += ","; all += kv.first; }
+    if (all.size() + 1 > cap) return ZKW_ERR_INVALID;
+    memcpy(buf, all.c_str(), all.size() + 1);
     return ZKW_OK;
 }
 
@@ -243,6 +317,37 @@ int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagr
         ZKW_CUDA(ctx, cudaMemcpyAsync(b.points, srcs[i], n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
         ZKW_TRY(msm_prepare_basis(ctx, b));
     }
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+int zkw_srs_setup(zkw_ctx* ctx, unsigned k, const uint64_t tau[4]) {
+    CTX_ENTER(ctx);
+    if (!tau) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return srs_setup(ctx, k, tau);
+}
+
+int zkw_srs_get(zkw_ctx* ctx, int which_bases, uint64_t* out_xy, size_t n) {
+    CTX_ENTER(ctx);
+    if (which_bases != ZKW_BASES_G && which_bases != ZKW_BASES_G_LAGRANGE) return ZKW_ERR_INVALID;
+    MsmBasis& b = ctx->bases[which_bases];
+    if (!b.points) return ZKW_ERR_STATE;
+    if (!out_xy || n > b.n) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out_xy, b.points, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
+int zkw_g1_fixed_base_mul(zkw_ctx* ctx, const uint64_t* scalars, size_t n, uint64_t* out_xy) {
+    CTX_ENTER(ctx);
+    if ((!scalars || !out_xy) && n) return ZKW_ERR_INVALID;
+    if (n == 0) return ZKW_OK;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, n * 32));
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_b, n * 64));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    ZKW_TRY(fixed_base_mul_dev(ctx, (const uint64_t*)ctx->io_a.ptr, n, (uint64_t*)ctx->io_b.ptr));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out_xy, ctx->io_b.ptr, n * 64, cudaMemcpyDeviceToHost, ctx->stream));
     ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZKW_OK;
 }

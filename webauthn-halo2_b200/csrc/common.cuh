@@ -57,6 +57,13 @@ struct zkw_ctx {
     zkw::DeviceBuffer ptr_table;         // device copy of the quotient pointer tables
     void* pinned = nullptr;              // small pinned host area for results
     size_t pinned_bytes = 0;
+
+    // optional per-kernel timing (CUDA events on the ctx stream), off by default
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t start, stop; };
+    std::vector<ProfRec> prof_pending;
+    std::map<std::string, std::pair<double, uint64_t>> prof_totals;  // name -> (ms, launches)
+    std::vector<cudaEvent_t> event_pool;
 };
 
 namespace zkw {
@@ -84,6 +91,14 @@ int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes);
         if (_e != cudaSuccess) return zkw::set_cuda_error(ctx, _e, "kernel launch"); \
     } while (0)
 
+// RAII bracket around one kernel launch: records start/stop events when ctx->profiling is on.
+struct ProfScope {
+    zkw_ctx* ctx;
+    cudaEvent_t stop = nullptr;
+    ProfScope(zkw_ctx* c, const char* name);
+    ~ProfScope();
+};
+
 // ---- entry points implemented per translation unit (device pointers, async on ctx->stream) ----
 // ntt.cu
 int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, const uint64_t** out_dev);
@@ -97,6 +112,9 @@ int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint
 int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
 void msm_free_basis(MsmBasis& b);
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);
+// srs.cu
+int srs_setup(zkw_ctx* ctx, unsigned k, const uint64_t tau_m[4]);
+int fixed_base_mul_dev(zkw_ctx* ctx, const uint64_t* scalars_dev, size_t n, uint64_t* out_xy_dev);
 // quotient.cu
 int quotient_run(zkw_ctx* ctx, const zkw_quotient_inputs* in /* device vectors */, uint64_t* h_ext_dev);
 

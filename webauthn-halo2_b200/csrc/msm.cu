@@ -290,7 +290,7 @@ __global__ void g1_normalize_kernel(const uint4* __restrict__ xyz, uint4* __rest
 
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev) {
     if (m == 0) return ZKW_OK;
-    g1_normalize_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>((const uint4*)xyz_dev, (uint4*)out_xy_dev, m);
+    { ProfScope ps_(ctx, "g1_normalize_kernel"); g1_normalize_kernel<<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>((const uint4*)xyz_dev, (uint4*)out_xy_dev, m); }
     ZKW_LAUNCHED(ctx);
     return ZKW_OK;
 }
@@ -324,7 +324,7 @@ int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b) {
     if (b.table) { cudaFree(b.table); b.table = nullptr; }
     cudaError_t e = cudaMalloc((void**)&b.table, (size_t)p.windows * b.n * 64);
     if (e != cudaSuccess) { b.table = nullptr; cudaGetLastError(); return ZKW_OK; }  // fall back to per-window groups
-    msm_table_kernel<32><<<(unsigned)((b.n + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)b.points, (uint4*)b.table, b.n, c, p.windows);
+    { ProfScope ps_(ctx, "msm_table_kernel"); msm_table_kernel<32><<<(unsigned)((b.n + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)b.points, (uint4*)b.table, b.n, c, p.windows); }
     ZKW_LAUNCHED(ctx);
     b.c = c;
     b.windows = p.windows;
@@ -408,19 +408,19 @@ int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint
     cudaStream_t st = ctx->stream;
     // counts and cursor are adjacent: one memset
     ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
-    msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb);
+    { ProfScope ps_(ctx, "msm_recode_kernel"); msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb); }
     ZKW_LAUNCHED(ctx);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, tb);
+    { ProfScope ps_(ctx, "msm_scan_kernel"); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, tb); }
     ZKW_LAUNCHED(ctx);
-    msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0);
+    { ProfScope ps_(ctx, "msm_scatter_kernel"); msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0); }
     ZKW_LAUNCHED(ctx);
-    msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb);
+    { ProfScope ps_(ctx, "msm_accumulate_kernel"); msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    msm_combine_kernel<<<(unsigned)((tb * kCombineLanes + 127) / 128), 128, 0, st>>>(partials, slices, buckets, (uint32_t)tb);
+    { ProfScope ps_(ctx, "msm_combine_kernel"); msm_combine_kernel<<<(unsigned)((tb * kCombineLanes + 127) / 128), 128, 0, st>>>(partials, slices, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c);
+    { ProfScope ps_(ctx, "msm_bitreduce_kernel"); msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c); }
     ZKW_LAUNCHED(ctx);
-    msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs);
+    { ProfScope ps_(ctx, "msm_bitreduce_final_kernel"); msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs); }
     ZKW_LAUNCHED(ctx);
     const size_t out_bytes = (size_t)p.groups * c * 128;
     if (ctx->pinned_bytes < out_bytes) {

@@ -195,7 +195,7 @@ int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, cons
     ZKW_TRY(ensure_buffer(ctx, buf, (size_t)count * 32));
     const unsigned run = 64;
     const unsigned threads = (count + run - 1) / run;
-    twiddle_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>((uint4*)buf.ptr, fr_from_host(omega), count, run);
+    { ProfScope ps_(ctx, "twiddle_kernel"); twiddle_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>((uint4*)buf.ptr, fr_from_host(omega), count, run); }
     ZKW_LAUNCHED(ctx);
     ctx->twiddles[key] = buf;
     *out_dev = (const uint64_t*)buf.ptr;
@@ -209,7 +209,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     if (log_n == 0) {
         Fr s0 = Fr::one(), s1 = s0, s2 = s0;
         if (scale3) { s0 = fr_from_host(scale3); s1 = fr_from_host(scale3 + 4); s2 = fr_from_host(scale3 + 8); }
-        scale_kernel<<<1, 32, 0, ctx->stream>>>((const uint4*)src_dev, (uint4*)dst_dev, 1, s0, s1, s2, scale3 != nullptr);
+        { ProfScope ps_(ctx, "scale_kernel"); scale_kernel<<<1, 32, 0, ctx->stream>>>((const uint4*)src_dev, (uint4*)dst_dev, 1, s0, s1, s2, scale3 != nullptr); }
         ZKW_LAUNCHED(ctx);
         return ZKW_OK;
     }
@@ -259,7 +259,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         a.src = (const uint4*)cur_src;
         a.dst = (uint4*)out;
         const unsigned tiles = (unsigned)(n >> a.tl);
-        ntt_pass_kernel<<<tiles, kNttThreads, 0, ctx->stream>>>(a);
+        { ProfScope ps_(ctx, "ntt_pass_kernel"); ntt_pass_kernel<<<tiles, kNttThreads, 0, ctx->stream>>>(a); }
         ZKW_LAUNCHED(ctx);
         cur_src = out;
         s0 += B;

@@ -193,7 +193,7 @@ int quotient_run(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext_de
     q.one = Fr::one();
     for (unsigned i = 0; i < q.rot_scale; i++) q.t_evals[i] = fr_host(dc.t_evals[i]);
     const size_t en = (size_t)1 << sh.ext_k;
-    quotient_kernel<<<(unsigned)((en + 127) / 128), 128, 0, ctx->stream>>>(q);
+    { ProfScope ps_(ctx, "quotient_kernel"); quotient_kernel<<<(unsigned)((en + 127) / 128), 128, 0, ctx->stream>>>(q); }
     ZKW_LAUNCHED(ctx);
     return ZKW_OK;
 }

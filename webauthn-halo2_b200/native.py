@@ -42,7 +42,8 @@ EXPORTS = [
     "zkw_ntt_bn254_fr_dev", "zkw_lagrange_to_coeff", "zkw_lagrange_to_coeff_dev", "zkw_coeff_to_lagrange",
     "zkw_coeff_to_lagrange_dev", "zkw_coeff_to_extended", "zkw_coeff_to_extended_dev", "zkw_extended_to_coeff",
     "zkw_extended_to_coeff_dev", "zkw_quotient_ecdsa", "zkw_quotient_ecdsa_dev", "zkw_dev_alloc", "zkw_dev_free",
-    "zkw_memcpy_h2d", "zkw_memcpy_d2h",
+    "zkw_memcpy_h2d", "zkw_memcpy_d2h", "zkw_srs_setup", "zkw_srs_get", "zkw_g1_fixed_base_mul",
+    "zkw_profile_enable", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
 ]
 
 
@@ -118,6 +119,8 @@ def load_library() -> C.CDLL:
     lib.zkw_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
     lib.zkw_ctx_destroy.argtypes = [C.c_void_p]
     lib.zkw_ctx_destroy.restype = None
+    lib.zkw_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.zkw_profile_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     _lib = lib
     return lib
 
@@ -192,7 +195,41 @@ class Context:
     def msm_config(self, window_bits: int = 0, precompute: bool = True):
         self._check(self.lib.zkw_msm_config(self.h, window_bits, int(precompute)), "zkw_msm_config")
 
+    # -- per-kernel device timing ------------------------------------------------------------------
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.zkw_profile_enable(self.h, int(on)), "zkw_profile_enable")
+
+    def profile_reset(self):
+        self._check(self.lib.zkw_profile_reset(self.h), "zkw_profile_reset")
+
+    def profile_read(self, kernel: str) -> tuple[float, int]:
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        self._check(self.lib.zkw_profile_read(self.h, kernel.encode(), C.byref(ms), C.byref(cnt)), "zkw_profile_read")
+        return ms.value, cnt.value
+
+    def profile_all(self) -> dict:
+        buf = C.create_string_buffer(4096)
+        self._check(self.lib.zkw_profile_names(self.h, buf, C.c_size_t(4096)), "zkw_profile_names")
+        names = [x for x in buf.value.decode().split(",") if x]
+        return {n: self.profile_read(n) for n in names}
+
     # -- SRS ----------------------------------------------------------------------------------
+    def srs_setup(self, k: int, tau: np.ndarray):
+        """gen_srs(k) analogue with an explicit tau (Montgomery form, (4,) uint64)."""
+        t = _as_u64(tau).reshape(4)
+        self._check(self.lib.zkw_srs_setup(self.h, C.c_uint(k), _p(t)), "zkw_srs_setup")
+
+    def srs_get(self, which: int, n: int) -> np.ndarray:
+        out = np.zeros((n, 8), dtype=np.uint64)
+        self._check(self.lib.zkw_srs_get(self.h, which, _p(out), C.c_size_t(n)), "zkw_srs_get")
+        return out
+
+    def fixed_base_mul(self, scalars: np.ndarray) -> np.ndarray:
+        s = _as_u64(scalars, 4)
+        out = np.zeros((s.shape[0], 8), dtype=np.uint64)
+        self._check(self.lib.zkw_g1_fixed_base_mul(self.h, _p(s), C.c_size_t(s.shape[0]), _p(out)), "zkw_g1_fixed_base_mul")
+        return out
+
     def srs_load(self, g: np.ndarray, g_lagrange: np.ndarray | None = None):
         g = _as_u64(g, 8)
         gl = _as_u64(g_lagrange, 8) if g_lagrange is not None else None
