@@ -193,6 +193,42 @@ typedef struct {
 int zkw_quotient_ecdsa(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext);
 int zkw_quotient_ecdsa_dev(zkw_ctx* ctx, const zkw_quotient_inputs* in, uint64_t* h_ext_dev);
 
+/* ---- keygen + create_proof on the device ------------------------------
+ * The callers of the hot path, widened onto the device: what the reference reaches through
+ *   download_keys      -> keygen_vk / keygen_pk                      (ecdsa_p256.rs:256-272)
+ *   generate_proof_evm -> create_proof<.., ProverGWC, EvmTranscript> (ecdsa_p256.rs:329-377)
+ *   generate_proof     -> create_proof<.., Blake2bWrite>             (ecdsa_p256.rs:379-427)
+ * The resident SRS (zkw_srs_load / zkw_srs_setup) must have exactly n = 2^k points. */
+typedef struct zkw_pk zkw_pk;
+
+/* fixed_values: [num_fixed constants, table, num_advice gate selectors, (q_lookup in selector mode)],
+ * each n*4 u64 Montgomery, host.  perm_mapping: one array per permutation column
+ * [constants.., gate advice.., lookup advice..], each n pairs (col', row') of u32 — the cycle
+ * successor mapping of halo2's keygen Assembly.  Everything derived (polys, extended cosets, sigma,
+ * l_0 / l_last / l_active, sorted lookup table, VK commitments) is computed and kept on the device. */
+int zkw_keygen(zkw_ctx* ctx, const zkw_circuit_shape* shape, const uint64_t* const* fixed_values,
+               const uint32_t* const* perm_mapping, zkw_pk** out);
+void zkw_pk_destroy(zkw_ctx* ctx, zkw_pk* pk);
+int zkw_pk_info(const zkw_pk* pk, uint32_t* num_fixed_cols, uint32_t* num_perm_cols);
+/* VK: commitments to the fixed and sigma columns (affine Montgomery, 8 u64 each) and the transcript
+ * digest (Montgomery Fr).  The digest is self-defined (upstream hashes the Rust Debug string of the
+ * pinned VK): Blake2b-512("Halo2-Verify-Key") over a canonical serialisation, mod r. */
+int zkw_pk_vk(const zkw_pk* pk, uint64_t* fixed_commitments_xy, uint64_t* perm_commitments_xy, uint64_t digest[4]);
+
+enum { ZKW_TRANSCRIPT_BLAKE2B = 0, ZKW_TRANSCRIPT_EVM = 1 };
+/* advice: [num_advice + num_lookup_advice] host arrays holding the first advice_rows[c] (<= n - 7)
+ * rows of each advice column (Montgomery); unassigned usable rows are zero, the last
+ * blinding_factors + 1 rows are blinding.  seed keys the blinding stream (upstream: OsRng).
+ * Multi-open is GWC under both transcripts.  out receives the proof bytes (*out_len), ZKW_ERR_INVALID
+ * if out_cap is too small (out_len is still set) or if a lookup input is not in the table. */
+int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
+                     uint64_t seed, int transcript, uint8_t* out, size_t out_cap, size_t* out_len);
+
+/* Fr vectors between canonical little-endian integers (< 2r accepted) and halo2curves' Montgomery form;
+ * host pointers, n elements of 4 u64. */
+int zkw_fr_to_mont(zkw_ctx* ctx, const uint64_t* canonical, uint64_t* out, size_t n);
+int zkw_fr_from_mont(zkw_ctx* ctx, const uint64_t* mont, uint64_t* out, size_t n);
+
 /* ---- device memory helpers for FFI callers that keep polynomials resident -------------------- */
 int zkw_dev_alloc(zkw_ctx* ctx, size_t bytes, void** out_dev);
 int zkw_dev_free(zkw_ctx* ctx, void* dev);

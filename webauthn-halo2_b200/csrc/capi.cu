@@ -124,6 +124,25 @@ static void profile_collect(zkw_ctx* ctx) {
     ctx->prof_pending.clear();
 }
 
+__global__ void mont_convert_kernel(const uint4* in, uint4* out, size_t n, int to_mont) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr v = Fr::load(in + 2 * i);
+    if (to_mont) { v.reduce_once(); v = v.to_mont(); } else v = v.from_mont();
+    v.store(out + 2 * i);
+}
+
+static int mont_convert(zkw_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n, int to_mont) {
+    if (n == 0) return ZKW_OK;
+    ZKW_TRY(ensure_buffer(ctx, ctx->io_a, n * 32));
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->io_a.ptr, in, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    { ProfScope ps_(ctx, "mont_convert_kernel"); mont_convert_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const uint4*)ctx->io_a.ptr, (uint4*)ctx->io_a.ptr, n, to_mont); }
+    ZKW_LAUNCHED(ctx);
+    ZKW_CUDA(ctx, cudaMemcpyAsync(out, ctx->io_a.ptr, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZKW_OK;
+}
+
 static int free_buffer(DeviceBuffer& b) {
     if (b.ptr) cudaFree(b.ptr);
     b.ptr = nullptr;
@@ -199,7 +218,7 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->twiddles) free_buffer(kv.second);
     free_buffer(ctx->ntt_scratch); free_buffer(ctx->msm_ws);
-    free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table);
+    free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table); free_buffer(ctx->arena);
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     profile_collect(ctx);
@@ -319,6 +338,17 @@ int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagr
     }
     ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZKW_OK;
+}
+
+int zkw_fr_to_mont(zkw_ctx* ctx, const uint64_t* canonical, uint64_t* out, size_t n) {
+    CTX_ENTER(ctx);
+    if ((!canonical || !out) && n) return ZKW_ERR_INVALID;
+    return mont_convert(ctx, canonical, out, n, 1);
+}
+int zkw_fr_from_mont(zkw_ctx* ctx, const uint64_t* mont, uint64_t* out, size_t n) {
+    CTX_ENTER(ctx);
+    if ((!mont || !out) && n) return ZKW_ERR_INVALID;
+    return mont_convert(ctx, mont, out, n, 0);
 }
 
 int zkw_srs_setup(zkw_ctx* ctx, unsigned k, const uint64_t tau[4]) {

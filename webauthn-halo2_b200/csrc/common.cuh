@@ -55,6 +55,8 @@ struct zkw_ctx {
     zkw::DeviceBuffer msm_ws;
     zkw::DeviceBuffer io_a, io_b, io_c;  // staging for the host-pointer entry points
     zkw::DeviceBuffer ptr_table;         // device copy of the quotient pointer tables
+    zkw::DeviceBuffer arena;             // per-proof scratch arena (prover.cu), grown to the high-water mark
+    size_t arena_off = 0, arena_virtual = 0, arena_need = 0;
     void* pinned = nullptr;              // small pinned host area for results
     size_t pinned_bytes = 0;
 

@@ -312,7 +312,9 @@ struct Fp {
     // a^e for a 64-bit exponent (square-and-multiply, MSB first)
     __host__ __device__ Fp pow(uint64_t e) const {
         Fp acc = one();
-        for (int i = 63; i >= 0; i--) {
+        int top = 63;
+        while (top >= 0 && !((e >> top) & 1)) top--;  // skip leading zeros
+        for (int i = top; i >= 0; i--) {
             acc = acc.sqr();
             if ((e >> i) & 1) acc = acc * *this;
         }

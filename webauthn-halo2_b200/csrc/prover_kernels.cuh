@@ -1,0 +1,417 @@
+// prover_kernels.cuh — device kernels for the parts of halo2's create_proof that sit between the MSM /
+// NTT / quotient calls: blinding rows, the lookup argument's permuted columns, the
+// permutation / lookup grand products, polynomial evaluations at the challenge points, the GWC batching
+// and the (X - z) divisions.  All of it is streaming integer work over n x 32-byte vectors.
+//
+// Upstream functions these replace (halo2_proofs, PSE v2023_01_20; reached from the reference through
+// create_proof, halo2-circuits/src/ecc/ecdsa_p256.rs:366-373, 416-423, 555-562):
+//   plonk::lookup::prover::{commit_permuted -> permute_expression_pair, commit_product}
+//   plonk::permutation::prover::Argument::commit
+//   arithmetic::{eval_polynomial, kate_division}, poly::kzg::multiopen::gwc::ProverGWC::create_proof
+#pragma once
+#include "common.cuh"
+
+namespace zkw {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanBlock = kScanThreads * kScanPerThread;  // 2048 elements per CTA
+
+// ---- deterministic blinding stream (mirrors oracle/halo2_ref.py::rand_fr) ---------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ inline Fr rand_fr(uint64_t seed, uint64_t stream, uint64_t index) {
+    const uint64_t base = seed ^ splitmix64((stream << 32) ^ 0xA5A5A5A5ULL);
+    Fr v;
+    for (int j = 0; j < 4; j++) {
+        uint64_t w = splitmix64(base + 4 * index + j);
+        if (j == 3) w &= 0x3FFFFFFFFFFFFFFFULL;
+        v.l[2 * j] = (uint32_t)w;
+        v.l[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    v.reduce_once();  // < 2^254 < 2r
+    return v.to_mont();
+}
+
+__global__ void rand_fill_kernel(uint4* out, size_t count, uint64_t seed, uint64_t stream, uint64_t first_index) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    rand_fr(seed, stream, first_index + i).store(out + 2 * i);
+}
+
+__global__ void zero_fill_kernel(uint4* out, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[2 * i] = make_uint4(0, 0, 0, 0);
+    out[2 * i + 1] = make_uint4(0, 0, 0, 0);
+}
+
+// out[i] = a[i] * b[i]
+__global__ void mul_vec_kernel(const uint4* a, const uint4* b, uint4* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    (Fr::load(a + 2 * i) * Fr::load(b + 2 * i)).store(out + 2 * i);
+}
+
+// omega^i from the half-size twiddle table (omega^(i + n/2) = -omega^i)
+__device__ __forceinline__ Fr omega_pow(const uint4* tw, size_t i, size_t half) {
+    Fr w = Fr::load_nc(tw + 2 * (i & (half - 1)));
+    return (i & half) ? w.neg() : w;
+}
+
+// ---- grand-product numerators / denominators ------------------------------------------------------------
+struct PermChunkArgs {
+    const uint4* values[8];   // column values (Lagrange), this chunk
+    const uint4* sigmas[8];   // sigma values (Lagrange), this chunk
+    Fr delta_beta[8];         // delta^(global column index) * beta
+    int ncols;
+    Fr beta, gamma;
+    const uint4* tw;          // omega^i, i < n/2
+    size_t n;
+};
+
+// num[i] = prod_c (v_c + delta^c beta omega^i + gamma), den[i] = prod_c (v_c + beta sigma_c + gamma)
+__global__ void __launch_bounds__(128) perm_numden_kernel(const PermChunkArgs a, uint4* num, uint4* den) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const Fr w = omega_pow(a.tw, i, a.n >> 1);
+    Fr nu = Fr::one(), de = Fr::one();
+    for (int c = 0; c < a.ncols; c++) {
+        const Fr v = Fr::load(a.values[c] + 2 * i);
+        const Fr s = Fr::load_nc(a.sigmas[c] + 2 * i);
+        nu = nu * (v + a.delta_beta[c] * w + a.gamma);
+        de = de * (v + a.beta * s + a.gamma);
+    }
+    nu.store(num + 2 * i);
+    de.store(den + 2 * i);
+}
+
+// lookup: num = (input + beta)(table + gamma), den = (A' + beta)(S' + gamma)
+__global__ void __launch_bounds__(128) lookup_numden_kernel(const uint4* inp, const uint4* tab, const uint4* ap, const uint4* sp,
+                                                            Fr beta, Fr gamma, uint4* num, uint4* den, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ((Fr::load(inp + 2 * i) + beta) * (Fr::load_nc(tab + 2 * i) + gamma)).store(num + 2 * i);
+    ((Fr::load(ap + 2 * i) + beta) * (Fr::load(sp + 2 * i) + gamma)).store(den + 2 * i);
+}
+
+// ---- three-phase scans over field elements ------------------------------------------------------------------
+// MUL = true: running products, false: running sums.  REVERSE = true scans from the last element down.
+// Inclusive: out[i] = x[0] op ... op x[i]  (or x[i] op ... op x[n-1] when REVERSE).
+template <bool MUL>
+__device__ __forceinline__ Fr scan_op(const Fr& a, const Fr& b) { return MUL ? a * b : a + b; }
+template <bool MUL>
+__device__ __forceinline__ Fr scan_identity() { return MUL ? Fr::one() : Fr::zero(); }
+
+// phase 1: per-CTA totals
+template <bool MUL, bool REVERSE>
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint4* x, uint4* block_totals, size_t n) {
+    __shared__ uint4 sh[kScanThreads * 2];
+    const size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    Fr acc = scan_identity<MUL>();
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; j++) {
+        size_t i = base + j;
+        if (i < n) {
+            size_t idx = REVERSE ? n - 1 - i : i;
+            acc = scan_op<MUL>(acc, Fr::load(x + 2 * idx));
+        }
+    }
+    acc.store(sh + 2 * threadIdx.x);
+    __syncthreads();
+    for (int d = kScanThreads / 2; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) {
+            Fr a = Fr::load(sh + 2 * threadIdx.x), b = Fr::load(sh + 2 * (threadIdx.x + d));
+            scan_op<MUL>(a, b).store(sh + 2 * threadIdx.x);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        block_totals[2 * blockIdx.x] = sh[0];
+        block_totals[2 * blockIdx.x + 1] = sh[1];
+    }
+}
+
+// phase 2: one CTA turns the block totals into exclusive block prefixes (in place); also emits the grand total
+template <bool MUL>
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(uint4* block_totals, size_t nblocks, uint4* grand_total) {
+    __shared__ uint4 sh[1024 * 2];
+    const int t = threadIdx.x;
+    const size_t per = (nblocks + 1023) / 1024;
+    const size_t lo = (size_t)t * per, hi = lo + per < nblocks ? lo + per : nblocks;
+    Fr acc = scan_identity<MUL>();
+    for (size_t i = lo; i < hi; i++) acc = scan_op<MUL>(acc, Fr::load(block_totals + 2 * i));
+    acc.store(sh + 2 * t);
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        Fr v = scan_identity<MUL>();
+        const bool has = t >= d;
+        if (has) v = Fr::load(sh + 2 * (t - d));
+        __syncthreads();
+        if (has) scan_op<MUL>(v, Fr::load(sh + 2 * t)).store(sh + 2 * t);
+        __syncthreads();
+    }
+    Fr run = t == 0 ? scan_identity<MUL>() : Fr::load(sh + 2 * (t - 1));  // exclusive prefix of this thread's run
+    for (size_t i = lo; i < hi; i++) {
+        Fr cur = Fr::load(block_totals + 2 * i);
+        run.store(block_totals + 2 * i);
+        run = scan_op<MUL>(run, cur);
+    }
+    if (t == 1023 && grand_total) {
+        grand_total[0] = sh[2 * 1023];
+        grand_total[1] = sh[2 * 1023 + 1];
+    }
+}
+
+// phase 3: inclusive scan within the CTA, offset by the CTA's exclusive prefix
+template <bool MUL, bool REVERSE>
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint4* x, const uint4* block_prefix, uint4* out, size_t n) {
+    __shared__ uint4 sh[kScanThreads * 2];
+    const size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    Fr v[kScanPerThread];
+    Fr acc = scan_identity<MUL>();
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; j++) {
+        size_t i = base + j;
+        if (i < n) {
+            size_t idx = REVERSE ? n - 1 - i : i;
+            acc = scan_op<MUL>(acc, Fr::load(x + 2 * idx));
+        }
+        v[j] = acc;
+    }
+    acc.store(sh + 2 * threadIdx.x);
+    __syncthreads();
+    for (int d = 1; d < kScanThreads; d <<= 1) {
+        Fr u = scan_identity<MUL>();
+        const bool has = (int)threadIdx.x >= d;
+        if (has) u = Fr::load(sh + 2 * (threadIdx.x - d));
+        __syncthreads();
+        if (has) scan_op<MUL>(u, Fr::load(sh + 2 * threadIdx.x)).store(sh + 2 * threadIdx.x);
+        __syncthreads();
+    }
+    Fr pre = Fr::load(block_prefix + 2 * blockIdx.x);
+    if (threadIdx.x > 0) pre = scan_op<MUL>(pre, Fr::load(sh + 2 * (threadIdx.x - 1)));
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; j++) {
+        size_t i = base + j;
+        if (i < n) {
+            size_t idx = REVERSE ? n - 1 - i : i;
+            scan_op<MUL>(pre, v[j]).store(out + 2 * idx);
+        }
+    }
+}
+
+// z[0] = z0; z[i+1] = z0 * PN[i] * SD[i+1] * Tinv for i+1 <= u (SD[n] = 1); rows above u are blinding rows
+// PN = inclusive prefix products of num, SD = inclusive suffix products of den, T = SD[0].
+__global__ void __launch_bounds__(128) grand_product_finalize_kernel(const uint4* pn, const uint4* sd, const uint4* z0_ptr, Fr tinv,
+                                                                     uint4* z, size_t u, size_t n) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > u) return;
+    const Fr z0 = z0_ptr ? Fr::load(z0_ptr) : Fr::one();
+    if (r == 0) { z0.store(z); return; }
+    Fr s = r < n ? Fr::load(sd + 2 * r) : Fr::one();
+    (z0 * tinv * Fr::load(pn + 2 * (r - 1)) * s).store(z + 2 * r);
+}
+
+// ---- lookup argument: permuted input / table ---------------------------------------------------------------
+// 256-bit compare of canonical little-endian values
+__device__ __forceinline__ int cmp256(const Fr& a, const Fr& b) {
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (a.l[i] != b.l[i]) return a.l[i] < b.l[i] ? -1 : 1;
+    }
+    return 0;
+}
+
+// rank[i] = index of input value i in the sorted distinct table (canonical form); histogram of ranks
+__global__ void lookup_rank_kernel(const uint4* inp, const uint4* table_sorted_canon, uint32_t m, uint32_t* rank, uint32_t* counts,
+                                   uint32_t* error_flag, size_t u) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= u) return;
+    const Fr v = Fr::load(inp + 2 * i).from_mont();
+    uint32_t lo = 0, hi = m;  // first index with table[idx] >= v
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)mid), v) < 0) lo = mid + 1; else hi = mid;
+    }
+    if (lo >= m || cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)lo), v) != 0) {
+        atomicExch(error_flag, 1u);  // ConstraintSystemFailure upstream: lookup input not in table
+        rank[i] = 0;
+        return;
+    }
+    rank[i] = lo;
+    atomicAdd(&counts[lo], 1u);
+}
+
+// three exclusive scans over the m distinct table values in one single-CTA kernel:
+//   run_start[j]  = sum_{j'<j} c[j']                       (start row of value j's run in A')
+//   rep_start[j]  = sum_{j'<j} max(c[j']-1, 0)              (index of its first repeated row)
+//   desc_start[q] = sum_{q'<q} left[m-1-q'],  left[j] = mult[j] - (c[j] > 0)   (leftovers, descending value order)
+__global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m, uint32_t* run_start,
+                                                           uint32_t* rep_start, uint32_t* desc_start, uint32_t* error_flag) {
+    __shared__ uint32_t sa[1024], sb[1024], sc[1024];
+    const int t = threadIdx.x;
+    const uint32_t per = (m + 1023) / 1024;
+    const uint32_t lo = min(m, (uint32_t)t * per), hi = min(m, lo + per);
+    uint32_t a = 0, b = 0, c = 0;
+    for (uint32_t j = lo; j < hi; j++) {
+        const uint32_t cj = counts[j];
+        a += cj;
+        b += cj ? cj - 1 : 0;
+        const uint32_t jj = m - 1 - j;  // descending position handled by this thread in mirrored order
+        const uint32_t cjj = counts[jj], mu = mult[jj];
+        if (cjj && mu == 0) atomicExch(error_flag, 1u);
+        c += mu - (cjj ? 1u : 0u);
+    }
+    sa[t] = a; sb[t] = b; sc[t] = c;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t va = 0, vb = 0, vc = 0;
+        if (t >= d) { va = sa[t - d]; vb = sb[t - d]; vc = sc[t - d]; }
+        __syncthreads();
+        sa[t] += va; sb[t] += vb; sc[t] += vc;
+        __syncthreads();
+    }
+    uint32_t ra = sa[t] - a, rb = sb[t] - b, rc = sc[t] - c;
+    for (uint32_t j = lo; j < hi; j++) {
+        const uint32_t cj = counts[j];
+        run_start[j] = ra; rep_start[j] = rb;
+        ra += cj; rb += cj ? cj - 1 : 0;
+        const uint32_t jj = m - 1 - j;
+        desc_start[j] = rc;  // desc_start is indexed by descending position q = j
+        rc += mult[jj] - (counts[jj] ? 1u : 0u);
+    }
+    if (t == 1023) { run_start[m] = sa[1023]; rep_start[m] = sb[1023]; desc_start[m] = sc[1023]; }
+}
+
+// last index q in [0, m) with start[q] <= x  (starts non-decreasing, start[m] = total > x)
+__device__ __forceinline__ uint32_t last_le(const uint32_t* start, uint32_t m, uint32_t x) {
+    uint32_t lo = 0, hi = m;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (start[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// A'[r] = value of the run containing row r; S'[r] = that value at the run's first row, else the
+// (rep index)-th leftover table value in DESCENDING value order (upstream pops repeated rows from the end
+// while walking the leftovers in ascending order).
+__global__ void lookup_expand_kernel(const uint4* table_sorted_mont, uint32_t m, const uint32_t* run_start, const uint32_t* rep_start,
+                                     const uint32_t* desc_start, uint4* a_out, uint4* s_out, size_t u) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= u) return;
+    const uint32_t j = last_le(run_start, m, (uint32_t)r);
+    const uint4 v0 = table_sorted_mont[2 * (size_t)j], v1 = table_sorted_mont[2 * (size_t)j + 1];
+    a_out[2 * r] = v0; a_out[2 * r + 1] = v1;
+    const uint32_t off = (uint32_t)r - run_start[j];
+    if (off == 0) {
+        s_out[2 * r] = v0; s_out[2 * r + 1] = v1;
+    } else {
+        const uint32_t q = rep_start[j] + off - 1;
+        const uint32_t dq = last_le(desc_start, m, q);
+        const uint32_t jj = m - 1 - dq;
+        s_out[2 * r] = table_sorted_mont[2 * (size_t)jj];
+        s_out[2 * r + 1] = table_sorted_mont[2 * (size_t)jj + 1];
+    }
+}
+
+// ---- batched polynomial evaluation -------------------------------------------------------------------------
+// One (poly, point) pair per blockIdx.y.  Level 0: each CTA reduces kScanBlock coefficients to
+// sum_i c_i x^(i - chunk_start) using per-thread Horner and a tree over threads with x^(8*2^l); the
+// per-CTA partials form a polynomial in x^2048 that the same kernel reduces at the next level.
+struct EvalJob {
+    const uint4* coeffs;   // level-0 input
+    uint32_t point;        // index into the power tables
+};
+// pow_table[point][l] = x^(2^l), l < 40
+__global__ void __launch_bounds__(kScanThreads) eval_reduce_kernel(const EvalJob* jobs, const uint4* level_base, size_t in_stride,
+                                                                  const uint4* pow_table, int log_stride, uint4* partial_out, size_t n,
+                                                                  size_t out_stride) {
+    __shared__ uint4 sh[kScanThreads * 2];
+    const EvalJob job = jobs[blockIdx.y];
+    const uint4* src = level_base ? level_base + 2 * (size_t)blockIdx.y * in_stride : job.coeffs;
+    const uint4* pw = pow_table + 2 * 40 * (size_t)job.point;
+    const Fr x1 = Fr::load(pw + 2 * log_stride);  // x^(2^log_stride): the variable at this level
+    const size_t base = (size_t)blockIdx.x * kScanBlock + (size_t)threadIdx.x * kScanPerThread;
+    Fr acc = Fr::zero();
+#pragma unroll
+    for (int j = kScanPerThread - 1; j >= 0; j--) {
+        size_t i = base + j;
+        Fr c = i < n ? Fr::load(src + 2 * i) : Fr::zero();
+        acc = acc * x1 + c;
+    }
+    acc.store(sh + 2 * threadIdx.x);
+    __syncthreads();
+    // tree: pair (t, t + d) with weight x1^(8 d); 8 = 2^3 coefficients per thread
+    int lvl = log_stride + 3;
+    for (int d = 1; d < kScanThreads; d <<= 1, lvl++) {
+        if ((threadIdx.x & (2 * d - 1)) == 0) {
+            Fr a = Fr::load(sh + 2 * threadIdx.x), b = Fr::load(sh + 2 * (threadIdx.x + d));
+            (a + b * Fr::load(pw + 2 * lvl)).store(sh + 2 * threadIdx.x);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint4* o = partial_out + 2 * ((size_t)blockIdx.y * out_stride + blockIdx.x);
+        o[0] = sh[0];
+        o[1] = sh[1];
+    }
+}
+
+// ---- linear combination: out[i] = sum_j w_j * p_j[i] ---------------------------------------------------------
+struct LinCombArgs {
+    const uint4* const* polys;  // device array of npolys pointers
+    const uint4* weights;       // device array of npolys field elements
+    int npolys;
+    size_t n;
+};
+__global__ void __launch_bounds__(128) lincomb_kernel(const LinCombArgs a, uint4* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Fr acc = Fr::zero();
+    for (int j = 0; j < a.npolys; j++) {
+        acc = acc + Fr::load_nc(a.weights + 2 * j) * Fr::load(a.polys[j] + 2 * i);
+    }
+    acc.store(out + 2 * i);
+}
+
+// ---- (p(X) - p(z)) / (X - z) --------------------------------------------------------------------------------
+// q_{i-1} = sum_{j >= i} a_j z^(j-i) = z^-i (p(z) - sum_{j<i} a_j z^j).  Step 1: t_j = a_j z^j.
+// Step 2: additive prefix scan of t (scan_*<false,false>).  Step 3: q_{i-1} = z^-i (E - PRE_{i-1}),
+// E = PRE_{n-1} = p(z).  z^j and z^-j are rebuilt per thread from a power seed (pow of a 64-bit exponent).
+__global__ void __launch_bounds__(128) kate_terms_kernel(const uint4* a, uint4* t, Fr z, size_t n) {
+    const size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (start >= n) return;
+    Fr p = z.pow((uint64_t)start);
+    for (size_t i = start; i < start + 16 && i < n; i++) {
+        (Fr::load(a + 2 * i) * p).store(t + 2 * i);
+        p = p * z;
+    }
+}
+// pre = inclusive prefix sums of t; q has n-1 entries: q[i-1] = zinv^i * (pre[n-1] - pre[i-1]) for i = 1..n-1
+__global__ void __launch_bounds__(128) kate_finish_kernel(const uint4* pre, uint4* q, Fr zinv, size_t n) {
+    const size_t start = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16 + 1;
+    if (start >= n) return;
+    const Fr e = Fr::load(pre + 2 * (n - 1));
+    Fr p = zinv.pow((uint64_t)start);
+    for (size_t i = start; i < start + 16 && i < n; i++) {
+        ((e - Fr::load(pre + 2 * (i - 1))) * p).store(q + 2 * (i - 1));
+        p = p * zinv;
+    }
+}
+
+// sigma values from the permutation mapping: sigma[c][r] = delta^(c') * omega^(r'), mapping as (c', r') u32 pairs
+__global__ void sigma_values_kernel(const uint2* mapping, const uint4* delta_pows, const uint4* tw, uint4* out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 m = mapping[i];
+    (Fr::load_nc(delta_pows + 2 * (size_t)m.x) * omega_pow(tw, m.y, n >> 1)).store(out + 2 * i);
+}
+
+}  // namespace zkw

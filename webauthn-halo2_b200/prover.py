@@ -1,0 +1,175 @@
+"""Host-side mirror of the reference's prover API (halo2-circuits/src/ecc/ecdsa_p256.rs) over the device
+prover of libzkw_b200.so:
+
+    download_keys(degree, pk_path, vk_path)                       ecdsa_p256.rs:256-272
+    generate_proof(pubkey_x, pubkey_y, r, s, msg_hash, pk_path, degree)      :379-427  (Blake2b transcript)
+    generate_proof_evm(...same...)                                           :329-377  (EVM transcript)
+
+Same argument meaning (five 32-byte little-endian canonical encodings + a proving-key path + degree) and
+error behaviour (ValueError where the reference `.unwrap()`s a failed from_bytes / from_xy).  Unlike the
+reference, which re-reads the SRS and proving key from disk on every request (ecdsa_p256.rs:338-343,
+388-393), keys stay resident on the GPU in a per-process cache keyed by (degree, proving_key_path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import native
+from .circuit import CircuitParams, SyntheticEcdsaCircuit, to_limbs, validate_assertion
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+TRANSCRIPT_BLAKE2B, TRANSCRIPT_EVM = 0, 1
+
+# development tau of the resident SRS (upstream's gen_srs draws it from a seeded RNG; any fixed value
+# gives a reproducible dev SRS — NOT a production ceremony)
+DEV_TAU_CANONICAL = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+
+
+class ProvingKey:
+    def __init__(self, ctx: native.Context, handle, shape: native.CircuitShape, circuit):
+        self.ctx, self.h, self.shape, self.circuit = ctx, handle, shape, circuit
+
+    def vk(self):
+        """(fixed commitments (nfixed, 8), permutation commitments (nperm, 8), digest (4,)) — Montgomery."""
+        lib = self.ctx.lib
+        nf, npm = C.c_uint32(0), C.c_uint32(0)
+        self.ctx._check(lib.zkw_pk_info(self.h, C.byref(nf), C.byref(npm)), "zkw_pk_info")
+        fx = np.zeros((nf.value, 8), dtype=np.uint64)
+        pm = np.zeros((npm.value, 8), dtype=np.uint64)
+        dg = np.zeros(4, dtype=np.uint64)
+        self.ctx._check(lib.zkw_pk_vk(self.h, fx.ctypes.data_as(u64p), pm.ctypes.data_as(u64p), dg.ctypes.data_as(u64p)), "zkw_pk_vk")
+        return fx, pm, dg
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.zkw_pk_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+def _bind(lib):
+    lib.zkw_keygen.argtypes = [C.c_void_p, C.POINTER(native.CircuitShape), C.POINTER(u64p), C.POINTER(u32p), C.POINTER(C.c_void_p)]
+    lib.zkw_pk_destroy.argtypes = [C.c_void_p, C.c_void_p]
+    lib.zkw_pk_destroy.restype = None
+    lib.zkw_pk_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.zkw_pk_vk.argtypes = [C.c_void_p, u64p, u64p, u64p]
+    lib.zkw_create_proof.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_uint64, C.c_int,
+                                     C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.zkw_fr_to_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+    lib.zkw_fr_from_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
+
+
+def fr_to_mont(ctx: native.Context, canonical: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(canonical, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(a)
+    _bind(ctx.lib)
+    ctx._check(ctx.lib.zkw_fr_to_mont(ctx.h, a.ctypes.data_as(u64p), out.ctypes.data_as(u64p), C.c_size_t(a.shape[0])), "zkw_fr_to_mont")
+    return out
+
+
+def fr_from_mont(ctx: native.Context, mont: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty_like(a)
+    _bind(ctx.lib)
+    ctx._check(ctx.lib.zkw_fr_from_mont(ctx.h, a.ctypes.data_as(u64p), out.ctypes.data_as(u64p), C.c_size_t(a.shape[0])), "zkw_fr_from_mont")
+    return out
+
+
+def keygen(ctx: native.Context, shape: native.CircuitShape, fixed_values: list[np.ndarray], mapping: list[np.ndarray], circuit=None) -> ProvingKey:
+    """keygen_vk + keygen_pk on the device.  fixed_values: Montgomery (n, 4) arrays; mapping: (n, 2) uint32."""
+    _bind(ctx.lib)
+    fv = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in fixed_values]
+    mp = [np.ascontiguousarray(a, dtype=np.uint32).reshape(-1, 2) for a in mapping]
+    ft = (u64p * len(fv))(*[a.ctypes.data_as(u64p) for a in fv])
+    mt = (u32p * len(mp))(*[a.ctypes.data_as(u32p) for a in mp])
+    h = C.c_void_p()
+    ctx._check(ctx.lib.zkw_keygen(ctx.h, C.byref(shape), ft, mt, C.byref(h)), "zkw_keygen")
+    return ProvingKey(ctx, h, shape, circuit)
+
+
+def create_proof(ctx: native.Context, pk: ProvingKey, advice: list[np.ndarray], seed: int, transcript: int) -> bytes:
+    """create_proof on the device.  advice: Montgomery (rows, 4) arrays, one per advice column."""
+    _bind(ctx.lib)
+    av = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in advice]
+    at = (u64p * len(av))(*[a.ctypes.data_as(u64p) for a in av])
+    rows = (C.c_size_t * len(av))(*[a.shape[0] for a in av])
+    cap = 1 << 20
+    buf = (C.c_uint8 * cap)()
+    n = C.c_size_t(0)
+    ctx._check(ctx.lib.zkw_create_proof(ctx.h, pk.h, at, rows, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), transcript, buf, cap, C.byref(n)),
+               "zkw_create_proof")
+    return bytes(buf[: n.value])
+
+
+# ---- reference-facing API ------------------------------------------------------------------------------
+class ProverState:
+    """Device-resident SRS + proving key for one (degree, config): what the reference keeps on disk as
+    ./params/kzg_bn254_<k>.srs and ./keys/proving_key.pk."""
+
+    def __init__(self, params: CircuitParams, device: int = 0, ctx: native.Context | None = None):
+        self.params = params
+        self.ctx = ctx or native.Context(device)
+        self.circuit = SyntheticEcdsaCircuit(params)
+        self.shape = native.CircuitShape.from_config(params.degree, params.num_advice, params.num_lookup_advice, params.num_fixed)
+        tau = fr_to_mont(self.ctx, np.array([[(DEV_TAU_CANONICAL >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]], dtype=np.uint64))[0]
+        self.ctx.srs_setup(params.degree, tau)                       # gen_srs(degree)
+        fixed = [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.fixed_columns()]
+        self.pk = keygen(self.ctx, self.shape, fixed, self.circuit.permutation_mapping(), self.circuit)   # keygen_vk + keygen_pk
+
+    def synthesize(self, assertion: bytes) -> list[np.ndarray]:
+        return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
+
+    def prove(self, assertion: bytes, transcript: int, seed: int | None = None) -> bytes:
+        if seed is None:
+            seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
+        return create_proof(self.ctx, self.pk, self.synthesize(assertion), seed, transcript)
+
+    def close(self):
+        self.pk.close()
+
+
+_STATES: dict = {}
+
+
+def _config_for(degree: int) -> CircuitParams:
+    """ECDSA_CONFIG env var (a path to the one-line JSON) or the reference's table for `degree`
+    (ecdsa_p256.rs:95-100 reads ./src/configs/ecdsa_circuit.config, which is the degree-17 line)."""
+    path = os.environ.get("ECDSA_CONFIG")
+    if path:
+        with open(path) as f:
+            p = CircuitParams.from_json(f.read())
+        if p.degree != degree:
+            raise ValueError(f"ECDSA_CONFIG is for degree {p.degree}, asked for {degree}")
+        return p
+    return CircuitParams.for_degree(degree)
+
+
+def download_keys(degree: int, proving_key_path: str | None = None, verifying_key_path: str | None = None, device: int = 0) -> ProverState:
+    """gen_srs + keygen_vk + keygen_pk (ecdsa_p256.rs:256-272), kept resident instead of written to disk."""
+    key = (degree, proving_key_path, device)
+    if key not in _STATES:
+        _STATES[key] = ProverState(_config_for(degree), device)
+    return _STATES[key]
+
+
+def _assertion_bytes(pubkey_x, pubkey_y, r, s, msg_hash) -> bytes:
+    validate_assertion(pubkey_x, pubkey_y, r, s, msg_hash)
+    return bytes(pubkey_x) + bytes(pubkey_y) + bytes(r) + bytes(s) + bytes(msg_hash)
+
+
+def generate_proof(pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg_hash: bytes, proving_key_path: str, degree: int,
+                   device: int = 0, seed: int | None = None) -> bytes:
+    """ecdsa_p256.rs:379-427 — Blake2b transcript."""
+    a = _assertion_bytes(pubkey_x, pubkey_y, r, s, msg_hash)
+    return download_keys(degree, proving_key_path, None, device).prove(a, TRANSCRIPT_BLAKE2B, seed)
+
+
+def generate_proof_evm(pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg_hash: bytes, proving_key_path: str, degree: int,
+                       device: int = 0, seed: int | None = None) -> bytes:
+    """ecdsa_p256.rs:329-377 — EVM (keccak) transcript, GWC multi-open."""
+    a = _assertion_bytes(pubkey_x, pubkey_y, r, s, msg_hash)
+    return download_keys(degree, proving_key_path, None, device).prove(a, TRANSCRIPT_EVM, seed)
