@@ -224,6 +224,12 @@ enum { ZKW_TRANSCRIPT_BLAKE2B = 0, ZKW_TRANSCRIPT_EVM = 1 };
 int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
                      uint64_t seed, int transcript, uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* flags: the advice arrays live in device memory / hold canonical integers (< 2r, little-endian u64
+ * limbs) that the device converts to Montgomery form. */
+enum { ZKW_ADVICE_ON_DEVICE = 1, ZKW_ADVICE_CANONICAL = 2 };
+int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
+                        uint64_t seed, int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+
 /* Fr vectors between canonical little-endian integers (< 2r accepted) and halo2curves' Montgomery form;
  * host pointers, n elements of 4 u64. */
 int zkw_fr_to_mont(zkw_ctx* ctx, const uint64_t* canonical, uint64_t* out, size_t n);

@@ -424,9 +424,18 @@ int zkw_pk_vk(const zkw_pk* pk, uint64_t* fixed_commitments_xy, uint64_t* perm_c
 // advice: [A + L] host arrays of advice_rows[c] <= usable rows field elements (Montgomery); the remaining
 // usable rows are zero (unassigned cells), the last blinding_factors+1 rows are blinding.
 // transcript: 0 = Blake2b/Challenge255 (compressed points), 1 = EVM/keccak (uncompressed).
+int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
+                        int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+
 int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
                      int transcript, uint8_t* out, size_t out_cap, size_t* out_len) {
+    return zkw_create_proof_ex(ctx, pk, advice, advice_rows, seed, transcript, 0u, out, out_cap, out_len);
+}
+
+int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
+                        int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!ctx || !pk || !advice || !advice_rows || !out_len || (transcript != 0 && transcript != 1)) return ZKW_ERR_INVALID;
+    const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL;
     ZKW_CUDA(ctx, cudaSetDevice(ctx->device));
     const zkw_circuit_shape& sh = pk->shape;
     const size_t n = pk->n, en = pk->en, u = pk->u, vb = n * 32, eb = en * 32;
@@ -445,7 +454,13 @@ int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advi
     std::vector<uint64_t*> adv(NA);
     for (unsigned c = 0; c < NA; c++) {
         ZKW_TRY(sc.get(vb, (void**)&adv[c]));
-        if (advice_rows[c]) ZKW_CUDA(ctx, cudaMemcpyAsync(adv[c], advice[c], advice_rows[c] * 32, cudaMemcpyHostToDevice, st));
+        if (advice_rows[c]) {
+            ZKW_CUDA(ctx, cudaMemcpyAsync(adv[c], advice[c], advice_rows[c] * 32, adv_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            if (adv_canonical) {
+                { ProfScope ps_(ctx, "to_mont_kernel"); to_mont_kernel<<<grid_for(advice_rows[c], 128), 128, 0, st>>>((uint4*)adv[c], advice_rows[c]); }
+                ZKW_LAUNCHED(ctx);
+            }
+        }
         if (u > advice_rows[c]) {
             { ProfScope ps_(ctx, "zero_fill_kernel"); zero_fill_kernel<<<grid_for(u - advice_rows[c], 128), 128, 0, st>>>((uint4*)(adv[c] + 4 * advice_rows[c]), u - advice_rows[c]); }
             ZKW_LAUNCHED(ctx);

@@ -51,6 +51,15 @@ __global__ void zero_fill_kernel(uint4* out, size_t count) {
     out[2 * i + 1] = make_uint4(0, 0, 0, 0);
 }
 
+// canonical little-endian integers (< 2r) -> Montgomery form, in place
+__global__ void to_mont_kernel(uint4* v, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    Fr x = Fr::load(v + 2 * i);
+    x.reduce_once();
+    x.to_mont().store(v + 2 * i);
+}
+
 // out[i] = a[i] * b[i]
 __global__ void mul_vec_kernel(const uint4* a, const uint4* b, uint4* out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

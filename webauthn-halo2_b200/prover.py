@@ -59,6 +59,8 @@ def _bind(lib):
     lib.zkw_pk_vk.argtypes = [C.c_void_p, u64p, u64p, u64p]
     lib.zkw_create_proof.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_uint64, C.c_int,
                                      C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.zkw_create_proof_ex.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_uint64, C.c_int, C.c_uint,
+                                        C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.zkw_fr_to_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
     lib.zkw_fr_from_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
 
@@ -91,17 +93,31 @@ def keygen(ctx: native.Context, shape: native.CircuitShape, fixed_values: list[n
     return ProvingKey(ctx, h, shape, circuit)
 
 
-def create_proof(ctx: native.Context, pk: ProvingKey, advice: list[np.ndarray], seed: int, transcript: int) -> bytes:
-    """create_proof on the device.  advice: Montgomery (rows, 4) arrays, one per advice column."""
+ADVICE_ON_DEVICE, ADVICE_CANONICAL = 1, 2
+_PROOF_CAP = 1 << 20
+
+
+def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, transcript: int, *, canonical: bool = False,
+                 device_rows: list[int] | None = None) -> bytes:
+    """create_proof on the device.  advice: one (rows, 4) uint64 array per advice column — host numpy arrays,
+    or (with device_rows given) device tensors / addresses.  canonical=True: values are plain integers that
+    the device converts to Montgomery form."""
     _bind(ctx.lib)
-    av = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in advice]
-    at = (u64p * len(av))(*[a.ctypes.data_as(u64p) for a in av])
-    rows = (C.c_size_t * len(av))(*[a.shape[0] for a in av])
-    cap = 1 << 20
-    buf = (C.c_uint8 * cap)()
+    flags = ADVICE_CANONICAL if canonical else 0
+    if device_rows is not None:
+        flags |= ADVICE_ON_DEVICE
+        at = (u64p * len(advice))(*[C.cast(native._addr(a), u64p) for a in advice])
+        rows = (C.c_size_t * len(advice))(*device_rows)
+        keep = advice
+    else:
+        keep = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in advice]
+        at = (u64p * len(keep))(*[a.ctypes.data_as(u64p) for a in keep])
+        rows = (C.c_size_t * len(keep))(*[a.shape[0] for a in keep])
+    buf = (C.c_uint8 * _PROOF_CAP)()
     n = C.c_size_t(0)
-    ctx._check(ctx.lib.zkw_create_proof(ctx.h, pk.h, at, rows, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), transcript, buf, cap, C.byref(n)),
-               "zkw_create_proof")
+    ctx._check(ctx.lib.zkw_create_proof_ex(ctx.h, pk.h, at, rows, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), transcript, flags, buf, _PROOF_CAP,
+                                           C.byref(n)), "zkw_create_proof_ex")
+    del keep
     return bytes(buf[: n.value])
 
 
@@ -124,9 +140,11 @@ class ProverState:
         return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
 
     def prove(self, assertion: bytes, transcript: int, seed: int | None = None) -> bytes:
+        """witness synthesis on the host, one H2D copy of the canonical advice values, proof bytes back."""
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
-        return create_proof(self.ctx, self.pk, self.synthesize(assertion), seed, transcript)
+        cols = [to_limbs(c) for c in self.circuit.synthesize(assertion)]
+        return create_proof(self.ctx, self.pk, cols, seed, transcript, canonical=True)
 
     def close(self):
         self.pk.close()
