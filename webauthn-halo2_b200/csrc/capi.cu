@@ -94,21 +94,22 @@ static cudaEvent_t take_event(zkw_ctx* ctx) {
     return e;
 }
 
-ProfScope::ProfScope(zkw_ctx* c, const char* name) : ctx(c) {
+ProfScope::ProfScope(zkw_ctx* c, const char* name, cudaStream_t s) : ctx(c), stream(s ? s : c->stream) {
     if (!c->profiling) return;
     cudaEvent_t start = take_event(c);
     stop = take_event(c);
     if (!start || !stop) { stop = nullptr; return; }
-    cudaEventRecord(start, c->stream);
+    cudaEventRecord(start, stream);
     c->prof_pending.push_back({name, start, stop});
 }
 ProfScope::~ProfScope() {
-    if (stop) cudaEventRecord(stop, ctx->stream);
+    if (stop) cudaEventRecord(stop, stream);
 }
 
 static void profile_collect(zkw_ctx* ctx) {
     if (ctx->prof_pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
+    for (int i = 1; i < zkw_ctx::kMsmLanes; i++) if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
     for (auto& r : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
@@ -222,6 +223,13 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     profile_collect(ctx);
+    for (int i = 0; i < zkw_ctx::kMsmLanes; i++) {
+        free_buffer(ctx->lane_ws[i]);
+        if (ctx->lane_pinned[i]) cudaFreeHost(ctx->lane_pinned[i]);
+        if (i && ctx->lane_stream[i]) cudaStreamDestroy(ctx->lane_stream[i]);
+        if (ctx->lane_done[i]) cudaEventDestroy(ctx->lane_done[i]);
+    }
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -53,6 +53,16 @@ struct zkw_ctx {
     // reusable scratch areas (grown on demand, never shrunk)
     zkw::DeviceBuffer ntt_scratch;
     zkw::DeviceBuffer msm_ws;
+    // MSM lanes: lane 0 runs on `stream`; lanes 1.. own a side stream so that the latency-bound tails of
+    // one MSM overlap the accumulation of the next (msm_run_batch)
+    static constexpr int kMsmLanes = 6;
+    cudaStream_t lane_stream[kMsmLanes] = {nullptr};
+    cudaEvent_t lane_done[kMsmLanes] = {nullptr};
+    cudaEvent_t fork_event = nullptr;
+    zkw::DeviceBuffer lane_ws[kMsmLanes];
+    void* lane_pinned[kMsmLanes] = {nullptr};
+    size_t lane_pinned_bytes[kMsmLanes] = {0};
+    int lane_groups[kMsmLanes] = {0}, lane_c[kMsmLanes] = {0};
     zkw::DeviceBuffer io_a, io_b, io_c;  // staging for the host-pointer entry points
     zkw::DeviceBuffer ptr_table;         // device copy of the quotient pointer tables
     zkw::DeviceBuffer arena;             // per-proof scratch arena (prover.cu), grown to the high-water mark
@@ -97,7 +107,8 @@ int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes);
 struct ProfScope {
     zkw_ctx* ctx;
     cudaEvent_t stop = nullptr;
-    ProfScope(zkw_ctx* c, const char* name);
+    cudaStream_t stream;
+    ProfScope(zkw_ctx* c, const char* name, cudaStream_t s = nullptr);
     ~ProfScope();
 };
 
@@ -111,6 +122,9 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
 // msm.cu
 int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
             uint64_t out_xyz_host[12]);
+struct MsmJob { int which_bases; const uint64_t* bases_dev; const uint64_t* scalars_dev; size_t n; };
+// up to zkw_ctx::kMsmLanes independent MSMs in flight at once; outs[i] = 12 u64 (x, y, 1) or Z = 0
+int msm_run_batch(zkw_ctx* ctx, const MsmJob* jobs, int count, uint64_t (*outs)[12]);
 int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
 void msm_free_basis(MsmBasis& b);
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);

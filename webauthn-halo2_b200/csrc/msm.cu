@@ -18,7 +18,8 @@
 //              affine point (two 128-bit loads per coordinate) while it adds the current one.  Work
 //              per thread is bounded whatever the scalar distribution (witness columns are far from
 //              uniform: zeros, bits, small limbs).
-//   combine    kCombineLanes lanes per bucket fold the bucket's slice sums (warp shuffles).
+//   combine    two levels: one thread folds up to kSlice2 slice sums; then one warp per bucket folds what
+//              is left (one copy for almost every bucket, a strided loop + shuffle tree for heavy ones).
 //   reduce     sum_b b * B_b  =  sum_j 2^j * S_j  with  S_j = sum of buckets whose index has bit j set:
 //              c independent tree sums, fully parallel; the final 2c-step Horner runs on the host
 //              in microseconds instead of as a latency-bound single-thread chain on the device.
@@ -30,7 +31,7 @@
 namespace zkw {
 
 constexpr int kSlice = 32;         // entries per accumulate thread
-constexpr int kCombineLanes = 8;   // lanes per bucket in the combine kernel
+constexpr int kSlice2 = 16;        // slice sums per second-level combine thread
 constexpr int kReduceBlocks = 16;  // CTAs per (group, bit) in the bit-sliced reduction
 constexpr int kReduceThreads = 128;
 
@@ -43,6 +44,7 @@ struct MsmPlan {
     size_t max_entries() const { return (size_t)windows * n; }
     size_t total_buckets() const { return (size_t)groups * nb; }
     size_t max_slices() const { return max_entries() / kSlice + total_buckets(); }
+    size_t max_slices2() const { return max_slices() / kSlice2 + total_buckets(); }
 };
 
 // ---- recode + histogram -----------------------------------------------------------------------
@@ -78,31 +80,70 @@ __global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* _
     }
 }
 
-// ---- single-CTA exclusive scans: bucket offsets and slice starts ------------------------------
+// ---- single-CTA exclusive scans: bucket offsets, slice starts, second-level slice starts -------
+// Tiles of 4096 counts (one uint4 per thread, coalesced); per tile a warp-shuffle scan of the thread
+// totals, a scan of the 32 warp totals, and a running carry.
+__device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                        uint32_t* __restrict__ slice_start, size_t total) {
-    __shared__ uint32_t sh_a[1024], sh_b[1024];
-    const int t = threadIdx.x;
-    const size_t per = (total + 1023) / 1024;
-    const size_t lo = (size_t)t * per, hi = lo + per < total ? lo + per : total;
-    uint32_t sa = 0, sb = 0;
-    for (size_t i = lo; i < hi; i++) { uint32_t cnt = counts[i]; sa += cnt; sb += (cnt + kSlice - 1) / kSlice; }
-    sh_a[t] = sa; sh_b[t] = sb;
+                                                        uint32_t* __restrict__ slice_start, uint32_t* __restrict__ slice2_start,
+                                                        size_t total) {
+    __shared__ uint32_t wsum[3][32];
+    __shared__ uint32_t carry[3];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 3) carry[t] = 0;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t va = 0, vb = 0;
-        if (t >= d) { va = sh_a[t - d]; vb = sh_b[t - d]; }
+    for (size_t base = 0; base < total; base += 4096) {
+        const size_t idx = base + 4 * (size_t)t;
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        if (idx + 3 < total) {
+            const uint4 v = *reinterpret_cast<const uint4*>(counts + idx);
+            cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
+        } else {
+            for (int j = 0; j < 4; j++) if (idx + j < total) cnt[j] = counts[idx + j];
+        }
+        uint32_t q[3][4], tot[3] = {0, 0, 0};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t s1 = (cnt[j] + kSlice - 1) / kSlice;
+            q[0][j] = cnt[j]; q[1][j] = s1; q[2][j] = (s1 + kSlice2 - 1) / kSlice2;
+            tot[0] += q[0][j]; tot[1] += q[1][j]; tot[2] += q[2][j];
+        }
+        uint32_t inc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            inc[k] = warp_inclusive_scan(tot[k], lane);
+            if (lane == 31) wsum[k][warp] = inc[k];
+        }
         __syncthreads();
-        sh_a[t] += va; sh_b[t] += vb;
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) wsum[k][lane] = warp_inclusive_scan(wsum[k][lane], lane);
+        }
+        __syncthreads();
+        uint32_t run[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) run[k] = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - tot[k];
+        uint32_t* outs[3] = {offsets, slice_start, slice2_start};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (idx + j < total) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { outs[k][idx + j] = run[k]; run[k] += q[k][j]; }
+            }
+        }
+        __syncthreads();
+        if (t < 3) carry[t] += wsum[t][31];
         __syncthreads();
     }
-    uint32_t ra = sh_a[t] - sa, rb = sh_b[t] - sb;  // exclusive prefix of this thread's run
-    for (size_t i = lo; i < hi; i++) {
-        uint32_t cnt = counts[i];
-        offsets[i] = ra; slice_start[i] = rb;
-        ra += cnt; rb += (cnt + kSlice - 1) / kSlice;
-    }
-    if (t == 1023) { offsets[total] = sh_a[1023]; slice_start[total] = sh_b[1023]; }
+    if (t == 0) { offsets[total] = carry[0]; slice_start[total] = carry[1]; slice2_start[total] = carry[2]; }
 }
 
 // ---- scatter entries into bucket order ----------------------------------------------------------
@@ -172,26 +213,61 @@ __device__ __forceinline__ G1Xyzz shfl_xor_point(const G1Xyzz& p, int lane_mask,
     return r;
 }
 
-// ---- combine: kCombineLanes lanes fold one bucket's slice sums --------------------------------------
-__global__ void __launch_bounds__(128) msm_combine_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ slice_start,
-                                                          uint4* __restrict__ buckets, uint32_t total_buckets) {
-    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t b = gt / kCombineLanes;
-    const int lane = gt % kCombineLanes;
-    G1Xyzz acc = G1Xyzz::identity();
-    if (b < total_buckets) {
-        const uint32_t s0 = slice_start[b], s1 = slice_start[b + 1];
-        for (uint32_t s = s0 + lane; s < s1; s += kCombineLanes) {
-            G1Xyzz p = G1Xyzz::load(partials + 8 * (size_t)s);
-            acc.add(p);
+// ---- combine, level 2: one thread folds up to kSlice2 slice sums of one bucket ----------------------
+__device__ __forceinline__ uint32_t last_start_le(const uint32_t* __restrict__ start, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;  // invariant: start[lo] <= x < start[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (start[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(128) msm_combine2_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ slice_start,
+                                                           const uint32_t* __restrict__ slice2_start, uint4* __restrict__ partials2,
+                                                           uint32_t total_buckets) {
+    const uint32_t sl2 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sl2 >= slice2_start[total_buckets]) return;
+    const uint32_t b = last_start_le(slice2_start, total_buckets, sl2);
+    const uint32_t begin = slice_start[b] + (sl2 - slice2_start[b]) * kSlice2;
+    const uint32_t bend = slice_start[b + 1];
+    const uint32_t end = begin + kSlice2 < bend ? begin + kSlice2 : bend;
+    G1Xyzz acc = G1Xyzz::load(partials + 8 * (size_t)begin);
+    for (uint32_t s = begin + 1; s < end; s++) {
+        G1Xyzz p = G1Xyzz::load(partials + 8 * (size_t)s);
+        acc.add(p);
+    }
+    acc.store(partials2 + 8 * (size_t)sl2);
+}
+
+// ---- combine, level 3: one warp per bucket folds whatever level-2 sums the bucket has -----------------
+// Almost every bucket has exactly one (copy) — only heavy buckets (skewed scalars: zeros, bits, tiny
+// digits of sorted lookup columns) reach the strided loop and the shuffle tree.
+__global__ void __launch_bounds__(128) msm_combine3_kernel(const uint4* __restrict__ partials2, const uint32_t* __restrict__ slice2_start,
+                                                           uint4* __restrict__ buckets, uint32_t total_buckets) {
+    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= total_buckets) return;  // whole warps leave together
+    const uint32_t s0 = slice2_start[b], s1 = slice2_start[b + 1];
+    if (s1 - s0 <= 1) {
+        if (lane < 8) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (s1 > s0) v = partials2[8 * (size_t)s0 + lane];
+            buckets[8 * (size_t)b + lane] = v;   // 128 bytes = 8 x uint4; all-zero is the identity (ZZ = 0)
         }
+        return;
+    }
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t s = s0 + lane; s < s1; s += 32) {
+        G1Xyzz p = G1Xyzz::load(partials2 + 8 * (size_t)s);
+        acc.add(p);
     }
 #pragma unroll
-    for (int m = kCombineLanes / 2; m >= 1; m >>= 1) {
+    for (int m = 16; m >= 1; m >>= 1) {
         G1Xyzz o = shfl_xor_point(acc, m, 0xffffffffu);
-        acc.add(o);
+        if (lane < m) acc.add(o);
     }
-    if (b < total_buckets && lane == 0) acc.store(buckets + 8 * (size_t)b);
+    if (lane == 0) acc.store(buckets + 8 * (size_t)b);
 }
 
 // ---- bit-sliced reduction: S[g][j] = sum over buckets of group g whose (index+1) has bit j ------------
@@ -355,14 +431,20 @@ static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, i
     memcpy(out_xyz + 8, z.l, 32);
 }
 
-int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
-            uint64_t out_xyz_host[12]) {
-    if (n == 0) {
-        memset(out_xyz_host, 0, 96);
-        Fq one = Fq::one();
-        memcpy(out_xyz_host + 4, one.l, 32);
-        return ZKW_OK;
-    }
+static int lane_init(zkw_ctx* ctx, int lane) {
+    if (!ctx->fork_event) ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    if (lane == 0) { ctx->lane_stream[0] = ctx->stream; }
+    else if (!ctx->lane_stream[lane]) ZKW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[lane], cudaStreamNonBlocking));
+    if (!ctx->lane_done[lane]) ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[lane], cudaEventDisableTiming));
+    return ZKW_OK;
+}
+
+// Enqueue one MSM on a lane's stream (no host synchronisation); results land in the lane's pinned slot.
+static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n) {
+    ZKW_TRY(lane_init(ctx, lane));
+    cudaStream_t st = ctx->lane_stream[lane];
+    ctx->lane_groups[lane] = 0;
+    if (n == 0) return ZKW_OK;
     const uint64_t* points = bases_dev;
     bool table = false;
     int c = pick_window_bits(ctx, n);
@@ -380,7 +462,7 @@ int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint
     if (p.max_entries() >= (1ull << 31)) return ZKW_ERR_INVALID;
     const size_t tb = p.total_buckets();
     const size_t max_slices = p.max_slices();
-    // workspace layout
+    const size_t max_slices2 = p.max_slices2();
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_digits = take(p.max_entries() * 4);
@@ -389,50 +471,103 @@ int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint
     const size_t o_cursor = take(tb * 4);
     const size_t o_offsets = take((tb + 1) * 4);
     const size_t o_slices = take((tb + 1) * 4);
+    const size_t o_slices2 = take((tb + 1) * 4);
     const size_t o_partials = take(max_slices * 128);
+    const size_t o_partials2 = take(max_slices2 * 128);
     const size_t o_buckets = take(tb * 128);
     const size_t o_blocks = take((size_t)p.groups * c * kReduceBlocks * 128);
     const size_t o_out = take((size_t)p.groups * c * 128);
-    ZKW_TRY(ensure_buffer(ctx, ctx->msm_ws, off));
-    char* ws = (char*)ctx->msm_ws.ptr;
+    DeviceBuffer& wsb = lane == 0 ? ctx->msm_ws : ctx->lane_ws[lane];
+    if (wsb.bytes < off) {
+        // growing a lane workspace frees memory other lanes' queued work does not touch, but cudaFree
+        // synchronises the device anyway; this only happens on the first MSM of a new size
+        if (wsb.ptr) { cudaDeviceSynchronize(); cudaFree(wsb.ptr); wsb.ptr = nullptr; wsb.bytes = 0; }
+        ZKW_CUDA(ctx, cudaMalloc(&wsb.ptr, off));
+        wsb.bytes = off;
+    }
+    char* ws = (char*)wsb.ptr;
     uint32_t* digits = (uint32_t*)(ws + o_digits);
     uint32_t* sorted = (uint32_t*)(ws + o_sorted);
     uint32_t* counts = (uint32_t*)(ws + o_counts);
     uint32_t* cursor = (uint32_t*)(ws + o_cursor);
     uint32_t* offsets = (uint32_t*)(ws + o_offsets);
     uint32_t* slices = (uint32_t*)(ws + o_slices);
+    uint32_t* slices2 = (uint32_t*)(ws + o_slices2);
     uint4* partials = (uint4*)(ws + o_partials);
+    uint4* partials2 = (uint4*)(ws + o_partials2);
     uint4* buckets = (uint4*)(ws + o_buckets);
     uint4* blocks = (uint4*)(ws + o_blocks);
     uint4* outs = (uint4*)(ws + o_out);
-    cudaStream_t st = ctx->stream;
-    // counts and cursor are adjacent: one memset
     ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
-    { ProfScope ps_(ctx, "msm_recode_kernel"); msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb); }
+    { ProfScope ps_(ctx, "msm_recode_kernel", st); msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_scan_kernel"); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, tb); }
+    { ProfScope ps_(ctx, "msm_scan_kernel", st); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, slices2, tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_scatter_kernel"); msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0); }
+    { ProfScope ps_(ctx, "msm_scatter_kernel", st); msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_accumulate_kernel"); msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb); }
+    { ProfScope ps_(ctx, "msm_accumulate_kernel", st); msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_combine_kernel"); msm_combine_kernel<<<(unsigned)((tb * kCombineLanes + 127) / 128), 128, 0, st>>>(partials, slices, buckets, (uint32_t)tb); }
+    { ProfScope ps_(ctx, "msm_combine2_kernel", st); msm_combine2_kernel<<<(unsigned)((max_slices2 + 127) / 128), 128, 0, st>>>(partials, slices, slices2, partials2, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_bitreduce_kernel"); msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c); }
+    { ProfScope ps_(ctx, "msm_combine3_kernel", st); msm_combine3_kernel<<<(unsigned)((tb * 32 + 127) / 128), 128, 0, st>>>(partials2, slices2, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_bitreduce_final_kernel"); msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs); }
+    { ProfScope ps_(ctx, "msm_bitreduce_kernel", st); msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c); }
+    ZKW_LAUNCHED(ctx);
+    { ProfScope ps_(ctx, "msm_bitreduce_final_kernel", st); msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs); }
     ZKW_LAUNCHED(ctx);
     const size_t out_bytes = (size_t)p.groups * c * 128;
-    if (ctx->pinned_bytes < out_bytes) {
-        if (ctx->pinned) cudaFreeHost(ctx->pinned);
-        ctx->pinned = nullptr;
-        ctx->pinned_bytes = 0;
-        ZKW_CUDA(ctx, cudaMallocHost(&ctx->pinned, out_bytes));
-        ctx->pinned_bytes = out_bytes;
+    if (ctx->lane_pinned_bytes[lane] < out_bytes) {
+        if (ctx->lane_pinned[lane]) cudaFreeHost(ctx->lane_pinned[lane]);
+        ctx->lane_pinned[lane] = nullptr;
+        ctx->lane_pinned_bytes[lane] = 0;
+        ZKW_CUDA(ctx, cudaMallocHost(&ctx->lane_pinned[lane], out_bytes));
+        ctx->lane_pinned_bytes[lane] = out_bytes;
     }
-    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, outs, out_bytes, cudaMemcpyDeviceToHost, st));
-    ZKW_CUDA(ctx, cudaStreamSynchronize(st));
-    msm_host_tail((const uint32_t*)ctx->pinned, p.groups, c, out_xyz_host);
+    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->lane_pinned[lane], outs, out_bytes, cudaMemcpyDeviceToHost, st));
+    ctx->lane_groups[lane] = p.groups;
+    ctx->lane_c[lane] = c;
+    return ZKW_OK;
+}
+
+static void msm_collect(zkw_ctx* ctx, int lane, uint64_t out_xyz[12]) {
+    if (ctx->lane_groups[lane] == 0) {  // empty MSM: identity
+        memset(out_xyz, 0, 96);
+        Fq one = Fq::one();
+        memcpy(out_xyz + 4, one.l, 32);
+        return;
+    }
+    msm_host_tail((const uint32_t*)ctx->lane_pinned[lane], ctx->lane_groups[lane], ctx->lane_c[lane], out_xyz);
+}
+
+int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
+            uint64_t out_xyz_host[12]) {
+    ZKW_TRY(msm_enqueue(ctx, 0, which_bases, bases_dev, scalars_dev, n));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    msm_collect(ctx, 0, out_xyz_host);
+    return ZKW_OK;
+}
+
+int msm_run_batch(zkw_ctx* ctx, const MsmJob* jobs, int count, uint64_t (*outs)[12]) {
+    int done = 0;
+    while (done < count) {
+        const int m = count - done < zkw_ctx::kMsmLanes ? count - done : zkw_ctx::kMsmLanes;
+        ZKW_TRY(lane_init(ctx, 0));
+        // side lanes start after everything queued so far on the main stream (their inputs live there)
+        ZKW_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+        for (int i = 0; i < m; i++) {
+            ZKW_TRY(lane_init(ctx, i));
+            if (i) ZKW_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[i], ctx->fork_event, 0));
+            const MsmJob& j = jobs[done + i];
+            ZKW_TRY(msm_enqueue(ctx, i, j.which_bases, j.bases_dev, j.scalars_dev, j.n));
+            if (i) {
+                ZKW_CUDA(ctx, cudaEventRecord(ctx->lane_done[i], ctx->lane_stream[i]));
+                ZKW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_done[i], 0));
+            }
+        }
+        ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < m; i++) msm_collect(ctx, i, outs[done + i]);
+        done += m;
+    }
     return ZKW_OK;
 }
 

@@ -179,6 +179,24 @@ static int commit_dev(zkw_ctx* ctx, int which, const uint64_t* scalars_dev, size
     return ZKW_OK;
 }
 
+// commit several polynomials at once (independent MSMs overlap on the context's lanes) and append the
+// commitments to the transcript in order
+static int commit_batch(zkw_ctx* ctx, Transcript& tr, const std::vector<std::pair<int, const uint64_t*>>& polys, size_t n) {
+    std::vector<MsmJob> jobs(polys.size());
+    for (size_t i = 0; i < polys.size(); i++) jobs[i] = MsmJob{polys[i].first, nullptr, polys[i].second, n};
+    std::vector<std::array<uint64_t, 12>> outs(polys.size());
+    ZKW_TRY(msm_run_batch(ctx, jobs.data(), (int)jobs.size(), reinterpret_cast<uint64_t(*)[12]>(outs.data())));
+    for (auto& o : outs) {
+        uint64_t xy[8];
+        memcpy(xy, o.data(), 64);
+        bool ident = true;
+        for (int i = 8; i < 12; i++) ident = ident && o[i] == 0;
+        if (ident) memset(xy, 0, 64);
+        tr.write_point(xy);
+    }
+    return ZKW_OK;
+}
+
 // inclusive scan of x (n elements) into out; MUL / REVERSE as in prover_kernels.cuh; tmp holds block totals
 template <bool MUL, bool REVERSE>
 static int scan_run(zkw_ctx* ctx, const uint64_t* x, uint64_t* out, size_t n, uint64_t* tmp_blocks, uint64_t* grand_total_dev) {
@@ -467,9 +485,10 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         }
         ZKW_TRY(rand_fill(ctx, adv[c] + 4 * u, n - u, seed, 1 + c, 0));
     }
-    for (unsigned c = 0; c < NA; c++) {
-        ZKW_TRY(commit_dev(ctx, ZKW_BASES_G_LAGRANGE, adv[c], n, pt));
-        tr.write_point(pt);
+    {
+        std::vector<std::pair<int, const uint64_t*>> polys;
+        for (unsigned c = 0; c < NA; c++) polys.push_back({ZKW_BASES_G_LAGRANGE, adv[c]});
+        ZKW_TRY(commit_batch(ctx, tr, polys, n));
     }
     const Fr theta = tr.squeeze();
     (void)theta;  // single-expression lookups: theta-compression is the identity
@@ -509,11 +528,10 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_LAUNCHED(ctx);
             ZKW_TRY(rand_fill(ctx, lk_a[l] + 4 * u, n - u, seed, 1000 + 2 * l, 0));
             ZKW_TRY(rand_fill(ctx, lk_s[l] + 4 * u, n - u, seed, 1001 + 2 * l, 0));
-            ZKW_TRY(commit_dev(ctx, ZKW_BASES_G_LAGRANGE, lk_a[l], n, pt));
-            tr.write_point(pt);
-            ZKW_TRY(commit_dev(ctx, ZKW_BASES_G_LAGRANGE, lk_s[l], n, pt));
-            tr.write_point(pt);
         }
+        std::vector<std::pair<int, const uint64_t*>> polys;
+        for (unsigned l = 0; l < nlk; l++) { polys.push_back({ZKW_BASES_G_LAGRANGE, lk_a[l]}); polys.push_back({ZKW_BASES_G_LAGRANGE, lk_s[l]}); }
+        ZKW_TRY(commit_batch(ctx, tr, polys, n));
     }
     const Fr beta = tr.squeeze();
     const Fr gamma = tr.squeeze();
@@ -548,15 +566,17 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         ZKW_LAUNCHED(ctx);
         ZKW_TRY(grand_product(ctx, num, den, pn, sd, blocks, total_dev, nullptr, lk_z[l], u, n, seed, 3000 + l));
     }
-    for (unsigned s = 0; s < nsets; s++) { ZKW_TRY(commit_dev(ctx, ZKW_BASES_G_LAGRANGE, perm_z[s], n, pt)); tr.write_point(pt); }
-    for (unsigned l = 0; l < nlk; l++) { ZKW_TRY(commit_dev(ctx, ZKW_BASES_G_LAGRANGE, lk_z[l], n, pt)); tr.write_point(pt); }
-
-    // ---- 5. vanishing argument: random polynomial ----
+    // ---- 5. vanishing argument: random polynomial; commitments of this round in one batch ----
     uint64_t* random_poly;
     ZKW_TRY(sc.get(vb, (void**)&random_poly));
     ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
-    ZKW_TRY(commit_dev(ctx, ZKW_BASES_G, random_poly, n, pt));
-    tr.write_point(pt);
+    {
+        std::vector<std::pair<int, const uint64_t*>> polys;
+        for (unsigned s = 0; s < nsets; s++) polys.push_back({ZKW_BASES_G_LAGRANGE, perm_z[s]});
+        for (unsigned l = 0; l < nlk; l++) polys.push_back({ZKW_BASES_G_LAGRANGE, lk_z[l]});
+        polys.push_back({ZKW_BASES_G, random_poly});
+        ZKW_TRY(commit_batch(ctx, tr, polys, n));
+    }
     const Fr y = tr.squeeze();
 
     // ---- 6. quotient ----
@@ -596,9 +616,10 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         ZKW_TRY(ntt_run(ctx, h_ext, sh.ext_k, h_ext, sh.ext_k, dom.dc.ext_omega_inv, false, dom.dc.ext_scale3));
     }
     const unsigned pieces = sh.cs_degree - 1;
-    for (unsigned i = 0; i < pieces; i++) {
-        ZKW_TRY(commit_dev(ctx, ZKW_BASES_G, h_ext + 4 * (size_t)i * n, n, pt));
-        tr.write_point(pt);
+    {
+        std::vector<std::pair<int, const uint64_t*>> polys;
+        for (unsigned i = 0; i < pieces; i++) polys.push_back({ZKW_BASES_G, h_ext + 4 * (size_t)i * n});
+        ZKW_TRY(commit_batch(ctx, tr, polys, n));
     }
     const Fr x = tr.squeeze();
 
@@ -708,10 +729,13 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     // ---- 8. multi-open (GWC) ----
     const Fr v = tr.squeeze();
     {
-        uint64_t *batch, *terms, *pre, *wit;
+        uint64_t *batch, *terms, *pre;
         ZKW_TRY(sc.get(vb, (void**)&batch)); ZKW_TRY(sc.get(vb, (void**)&terms));
-        ZKW_TRY(sc.get(vb, (void**)&pre)); ZKW_TRY(sc.get(vb, (void**)&wit));
+        ZKW_TRY(sc.get(vb, (void**)&pre));
+        std::vector<std::pair<int, const uint64_t*>> wpolys;
         for (int r : rots) {
+            uint64_t* wit;
+            ZKW_TRY(sc.get(vb, (void**)&wit));
             std::vector<const uint64_t*> ps;
             std::vector<Fr> ws;
             Fr pv = Fr::one();
@@ -725,9 +749,9 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_CUDA(ctx, cudaMemsetAsync(wit + 4 * (n - 1), 0, 32, st));
             { ProfScope ps_(ctx, "kate_finish_kernel"); kate_finish_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)pre, (uint4*)wit, zinv, n); }
             ZKW_LAUNCHED(ctx);
-            ZKW_TRY(commit_dev(ctx, ZKW_BASES_G, wit, n, pt));
-            tr.write_point(pt);
+            wpolys.push_back({ZKW_BASES_G, wit});
         }
+        ZKW_TRY(commit_batch(ctx, tr, wpolys, n));
     }
     *out_len = tr.out.size();
     if (!out || out_cap < tr.out.size()) return ZKW_ERR_INVALID;

@@ -261,41 +261,57 @@ __global__ void lookup_rank_kernel(const uint4* inp, const uint4* table_sorted_c
 //   run_start[j]  = sum_{j'<j} c[j']                       (start row of value j's run in A')
 //   rep_start[j]  = sum_{j'<j} max(c[j']-1, 0)              (index of its first repeated row)
 //   desc_start[q] = sum_{q'<q} left[m-1-q'],  left[j] = mult[j] - (c[j] > 0)   (leftovers, descending value order)
+// Tiles of 1024 entries, warp-shuffle scans, running carry (coalesced loads).
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m, uint32_t* run_start,
                                                            uint32_t* rep_start, uint32_t* desc_start, uint32_t* error_flag) {
-    __shared__ uint32_t sa[1024], sb[1024], sc[1024];
-    const int t = threadIdx.x;
-    const uint32_t per = (m + 1023) / 1024;
-    const uint32_t lo = min(m, (uint32_t)t * per), hi = min(m, lo + per);
-    uint32_t a = 0, b = 0, c = 0;
-    for (uint32_t j = lo; j < hi; j++) {
-        const uint32_t cj = counts[j];
-        a += cj;
-        b += cj ? cj - 1 : 0;
-        const uint32_t jj = m - 1 - j;  // descending position handled by this thread in mirrored order
-        const uint32_t cjj = counts[jj], mu = mult[jj];
-        if (cjj && mu == 0) atomicExch(error_flag, 1u);
-        c += mu - (cjj ? 1u : 0u);
-    }
-    sa[t] = a; sb[t] = b; sc[t] = c;
+    __shared__ uint32_t wsum[3][32];
+    __shared__ uint32_t carry[3];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < 3) carry[t] = 0;
     __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t va = 0, vb = 0, vc = 0;
-        if (t >= d) { va = sa[t - d]; vb = sb[t - d]; vc = sc[t - d]; }
+    for (uint32_t base = 0; base < m; base += 1024) {
+        const uint32_t j = base + t;
+        uint32_t q[3] = {0, 0, 0};
+        if (j < m) {
+            const uint32_t cj = counts[j];
+            q[0] = cj;
+            q[1] = cj ? cj - 1 : 0;
+            const uint32_t jj = m - 1 - j;
+            const uint32_t cjj = counts[jj], mu = mult[jj];
+            if (cjj && mu == 0) atomicExch(error_flag, 1u);
+            q[2] = mu - (cjj ? 1u : 0u);
+        }
+        uint32_t inc[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            inc[k] = warp_incl_scan_u32(q[k], lane);
+            if (lane == 31) wsum[k][warp] = inc[k];
+        }
         __syncthreads();
-        sa[t] += va; sb[t] += vb; sc[t] += vc;
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) wsum[k][lane] = warp_incl_scan_u32(wsum[k][lane], lane);
+        }
+        __syncthreads();
+        if (j < m) {
+            uint32_t* outs[3] = {run_start, rep_start, desc_start};
+#pragma unroll
+            for (int k = 0; k < 3; k++) outs[k][j] = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - q[k];
+        }
+        __syncthreads();
+        if (t < 3) carry[t] += wsum[t][31];
         __syncthreads();
     }
-    uint32_t ra = sa[t] - a, rb = sb[t] - b, rc = sc[t] - c;
-    for (uint32_t j = lo; j < hi; j++) {
-        const uint32_t cj = counts[j];
-        run_start[j] = ra; rep_start[j] = rb;
-        ra += cj; rb += cj ? cj - 1 : 0;
-        const uint32_t jj = m - 1 - j;
-        desc_start[j] = rc;  // desc_start is indexed by descending position q = j
-        rc += mult[jj] - (counts[jj] ? 1u : 0u);
-    }
-    if (t == 1023) { run_start[m] = sa[1023]; rep_start[m] = sb[1023]; desc_start[m] = sc[1023]; }
+    if (t == 0) { run_start[m] = carry[0]; rep_start[m] = carry[1]; desc_start[m] = carry[2]; }
 }
 
 // last index q in [0, m) with start[q] <= x  (starts non-decreasing, start[m] = total > x)
