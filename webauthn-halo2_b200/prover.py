@@ -150,6 +150,51 @@ class ProverState:
         self.pk.close()
 
 
+class ProverPool:
+    """Several ProverStates on ONE GPU proving independent assertions concurrently (the reference's batch
+    use: Rocket's worker threads each proving one request, proving-server/src/main.rs:49-79).  Each worker
+    owns a context (stream set, SRS tables, proving key, scratch arena); witness synthesis for the next
+    assertion overlaps the device work of the others, and the latency-bound phases of one proof overlap the
+    throughput-bound phases of another."""
+
+    def __init__(self, params: CircuitParams, device: int = 0, workers: int = 3):
+        self.states = [ProverState(params, device) for _ in range(workers)]
+
+    def prove_many(self, assertions: list[bytes], transcript: int, seed0: int = 0) -> list[bytes]:
+        import queue
+        import threading
+        todo: "queue.Queue[int]" = queue.Queue()
+        for i in range(len(assertions)):
+            todo.put(i)
+        out: list = [None] * len(assertions)
+        errors: list = []
+
+        def work(st: ProverState):
+            while True:
+                try:
+                    i = todo.get_nowait()
+                except queue.Empty:
+                    return
+                try:
+                    out[i] = st.prove(assertions[i], transcript, seed=seed0 + i)
+                except Exception as e:  # noqa: BLE001 - surfaced below
+                    errors.append(e)
+                    return
+
+        threads = [threading.Thread(target=work, args=(st,)) for st in self.states]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out
+
+    def close(self):
+        for st in self.states:
+            st.close()
+
+
 _STATES: dict = {}
 
 
