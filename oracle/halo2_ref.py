@@ -427,8 +427,111 @@ def kate_division(coeffs, z):
     return q
 
 
-def create_proof(pk: ProvingKey, g: np.ndarray, g_lagrange: np.ndarray, advice_in, seed: int, kind: str) -> bytes:
-    """advice_in: the advice columns' usable rows (lists of ints, length <= usable_rows each)."""
+def lagrange_interpolate(points, evals):
+    """coefficients of the unique polynomial of degree < len(points) through (points[i], evals[i])."""
+    m = len(points)
+    out = [0] * m
+    for i in range(m):
+        num = [1]
+        den = 1
+        for j in range(m):
+            if j == i:
+                continue
+            num = [(a - points[j] * b) % R for a, b in zip([0] + num, num + [0])]   # num * (X - p_j)
+            den = den * (points[i] - points[j]) % R
+        c = evals[i] * pow(den, -1, R) % R
+        for d in range(len(num)):
+            out[d] = (out[d] + c * num[d]) % R
+    return out
+
+
+def _shplonk_sets(queries, point_of):
+    """halo2_proofs::poly::kzg::multiopen::shplonk::construct_intermediate_sets restated.
+    queries: (rot, key, payload).  Returns (sets, super_points): sets in order of first appearance of
+    each distinct point set; inside a set the points are in ascending field order (BTreeSet) and the
+    commitments in order of first appearance."""
+    comm = []
+    super_points = set()
+    for rot, key, payload in queries:
+        pt = point_of(rot)
+        super_points.add(pt)
+        for e in comm:
+            if e[0] == key:
+                e[2].add(pt)
+                break
+        else:
+            comm.append((key, payload, {pt}))
+    sets = []
+    for key, payload, pts in comm:
+        sk = tuple(sorted(pts))
+        for st in sets:
+            if st[0] == sk:
+                st[1].append((key, payload))
+                break
+        else:
+            sets.append((sk, [(key, payload)]))
+    return sets, sorted(super_points)
+
+
+def shplonk_prove(tr, g, queries, point_of, n):
+    """ProverSHPLONK::create_proof restated.  queries: (rot, poly) with poly identity = list identity."""
+    y = tr.squeeze()
+    v = tr.squeeze()
+    sets, super_points = _shplonk_sets([(r, id(p), p) for r, p in queries], point_of)
+    interp = []
+    h_x = [0] * n
+    pv = 1
+    for points, polys in sets:
+        n_x = [0] * n
+        py = 1
+        rs = []
+        for _, poly in polys:
+            r_x = lagrange_interpolate(list(points), [poly_eval(poly, pt) for pt in points])
+            rs.append(r_x)
+            for i in range(n):
+                n_x[i] = (n_x[i] + py * (poly[i] - (r_x[i] if i < len(r_x) else 0))) % R
+            py = py * y % R
+        interp.append(rs)
+        q = n_x
+        for pt in points:
+            q = kate_division(q, pt)
+        q = q + [0] * (n - len(q))
+        h_x = [(a + pv * b) % R for a, b in zip(h_x, q)]
+        pv = pv * v % R
+    tr.write_point(commit(g, h_x))
+    u = tr.squeeze()
+    l_x = [0] * n
+    z_diffs = []
+    pv = 1
+    for (points, polys), rs in zip(sets, interp):
+        z_i = 1
+        for d in super_points:
+            if d not in points:
+                z_i = z_i * (u - d) % R
+        z_diffs.append(z_i)
+        py = 1
+        acc = [0] * n
+        for (_, poly), r_x in zip(polys, rs):
+            r_eval = poly_eval(r_x, u)
+            for i in range(n):
+                acc[i] = (acc[i] + py * poly[i]) % R
+            acc[0] = (acc[0] - py * r_eval) % R
+            py = py * y % R
+        l_x = [(a + pv * z_i % R * b) % R for a, b in zip(l_x, acc)]
+        pv = pv * v % R
+    zt = 1
+    for d in super_points:
+        zt = zt * (u - d) % R
+    l_x = [(a - zt * b) % R for a, b in zip(l_x, h_x)]
+    assert poly_eval(l_x, u) == 0
+    hq = kate_division(l_x, u)
+    inv0 = pow(z_diffs[0], -1, R)
+    tr.write_point(commit(g, [c * inv0 % R for c in hq]))
+
+
+def create_proof(pk: ProvingKey, g: np.ndarray, g_lagrange: np.ndarray, advice_in, seed: int, kind: str, multiopen: str = "gwc") -> bytes:
+    """advice_in: the advice columns' usable rows (lists of ints, length <= usable_rows each).
+    multiopen: "gwc" (ProverGWC, what generate_proof_evm uses) or "shplonk" (ProverSHPLONK, generate_proof)."""
     shape = pk.vk.shape
     dom = shape.domain()
     n, u = shape.n, shape.usable_rows
@@ -575,6 +678,9 @@ def create_proof(pk: ProvingKey, g: np.ndarray, g_lagrange: np.ndarray, advice_i
         queries.append((0, p))
     queries.append((0, h_poly))
     queries.append((0, random_poly))
+    if multiopen == "shplonk":
+        shplonk_prove(tr, g, queries, rot, n)
+        return bytes(tr.out)
     v = tr.squeeze()
     order = []
     for r, _ in queries:
@@ -597,7 +703,7 @@ def create_proof(pk: ProvingKey, g: np.ndarray, g_lagrange: np.ndarray, advice_i
 # ---------------------------------------------------------------------------------------------------
 # verifier
 # ---------------------------------------------------------------------------------------------------
-def verify_proof(vk: VerifyingKey, proof: bytes, kind: str, *, tau: int | None = None, g2_pair=None) -> bool:
+def verify_proof(vk: VerifyingKey, proof: bytes, kind: str, *, tau: int | None = None, g2_pair=None, multiopen: str = "gwc") -> bool:
     """halo2 verify_proof + VerifierGWC restated.  The final check is either the pairing
     e(left, [s]_2) == e(right, [1]_2) with g2_pair = (G2, sG2), or — with a development SRS whose tau is
     known — the equivalent G1 identity tau * left == right."""
@@ -706,6 +812,64 @@ def verify_proof(vk: VerifyingKey, proof: bytes, kind: str, *, tau: int | None =
         queries.append((0, pc, sigma_e[c]))
     queries.append((0, h_commit, h_eval))
     queries.append((0, random_c, random_e))
+
+    if multiopen == "shplonk":
+        # VerifierSHPLONK restated; a commitment's identity is its position in the query list's first use
+        keyed = []
+        seen = {}
+        for r, cm, ev in queries:
+            k = seen.setdefault(id(cm) if cm is not None else ("none", len(seen)), len(seen))
+            keyed.append((r, k, cm, ev))
+        point_of = lambda r: x * pow(omega, r, R) % R
+        y_ch = tr.squeeze()
+        v_ch = tr.squeeze()
+        try:
+            h1 = tr.read_point()
+            u_ch = tr.squeeze()
+            h2 = tr.read_point()
+        except (ValueError, IndexError):
+            return False
+        if tr.pos != len(proof):
+            return False
+        evals_of = {}
+        for r, k, cm, ev in keyed:
+            evals_of[(k, point_of(r))] = ev
+        sets, super_points = _shplonk_sets([(r, k, cm) for r, k, cm, ev in keyed], point_of)
+        outer = None
+        r_outer = 0
+        z_0 = z_0_diff_inv = 0
+        pv = 1
+        for i, (points, comms) in enumerate(sets):
+            z_diff = 1
+            for d in super_points:
+                if d not in points:
+                    z_diff = z_diff * (u_ch - d) % R
+            if i == 0:
+                z_0 = 1
+                for pt in points:
+                    z_0 = z_0 * (u_ch - pt) % R
+                z_0_diff_inv = pow(z_diff, -1, R)
+                z_diff = 1
+            else:
+                z_diff = z_diff * z_0_diff_inv % R
+            inner, r_inner, py = None, 0, 1
+            for k, cm in comms:
+                r_x = lagrange_interpolate(list(points), [evals_of[(k, pt)] for pt in points])
+                r_inner = (r_inner + py * poly_eval(r_x, u_ch)) % R
+                inner = g1_add(inner, g1_mul(cm, py))
+                py = py * y_ch % R
+            outer = g1_add(outer, g1_mul(inner, pv * z_diff % R))
+            r_outer = (r_outer + pv * r_inner % R * z_diff) % R
+            pv = pv * v_ch % R
+        right = g1_add(outer, g1_neg(g1_mul(vk.g0, r_outer)))
+        right = g1_add(right, g1_neg(g1_mul(h1, z_0)))
+        right = g1_add(right, g1_mul(h2, u_ch))
+        left = h2
+        if tau is not None:
+            return g1_mul(left, tau) == right
+        from . import pairing
+        g2, s_g2 = g2_pair
+        return pairing.pairing_product_is_one([(left, s_g2), (g1_neg(right), g2)])
 
     v = tr.squeeze()
     order = []

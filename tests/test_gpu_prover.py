@@ -44,8 +44,8 @@ def _oracle_vk(zkw, oracle, ctx, pk, oshape):
 
 
 @pytest.mark.parametrize("degree,A,L,F,lookup_bits", [(5, 1, 1, 1, 4), (6, 4, 1, 1, 5), (6, 2, 1, 2, 5), (7, 1, 1, 1, 6), (5, 8, 2, 1, 4)])
-@pytest.mark.parametrize("kind", ["evm", "blake2b"])
-def test_device_prover_matches_oracle_prover_bit_for_bit(zkw, oracle, degree, A, L, F, lookup_bits, kind):
+@pytest.mark.parametrize("kind,multiopen", [("evm", "gwc"), ("blake2b", "gwc"), ("blake2b", "shplonk"), ("evm", "shplonk")])
+def test_device_prover_matches_oracle_prover_bit_for_bit(zkw, oracle, degree, A, L, F, lookup_bits, kind, multiopen):
     from oracle import halo2_ref as h, synth_circuit as sc
     ctx = zkw.Context(0)
     try:
@@ -70,13 +70,14 @@ def test_device_prover_matches_oracle_prover_bit_for_bit(zkw, oracle, degree, A,
         # proofs
         advice_m = [oracle.fr_to_mont(col) for col in oadvice]
         t = zkw.TRANSCRIPT_EVM if kind == "evm" else zkw.TRANSCRIPT_BLAKE2B
-        proof = zkw.create_proof(ctx, pk, advice_m, seed=77, transcript=t)
-        want = h.create_proof(opk, g, gl, oadvice, seed=77, kind=kind)
+        sh = multiopen == "shplonk"
+        proof = zkw.create_proof(ctx, pk, advice_m, seed=77, transcript=t, shplonk=sh)
+        want = h.create_proof(opk, g, gl, oadvice, seed=77, kind=kind, multiopen=multiopen)
         assert proof == want
-        assert h.verify_proof(vk, proof, kind, tau=TAU)
+        assert h.verify_proof(vk, proof, kind, tau=TAU, multiopen=multiopen)
         # a second proof with another blinding seed differs and verifies; the context is reusable
-        other = zkw.create_proof(ctx, pk, advice_m, seed=78, transcript=t)
-        assert other != proof and h.verify_proof(vk, other, kind, tau=TAU)
+        other = zkw.create_proof(ctx, pk, advice_m, seed=78, transcript=t, shplonk=sh)
+        assert other != proof and h.verify_proof(vk, other, kind, tau=TAU, multiopen=multiopen)
         pk.close()
     finally:
         ctx.close()
@@ -113,8 +114,9 @@ def test_reference_api_k17_proof_layout_and_acceptance(zkw, oracle):
     oshape = h.Shape(17, 4, 1, 1)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
     assert h.verify_proof(vk, proof, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+    # generate_proof: Blake2b + SHPLONK — 1920 bytes, the size the reference publishes for this config (ecdsa_bench.csv:4)
     proof_b = zkw.generate_proof(x, y, r, s, m, "./keys/proving_key.pk", 17, seed=5)
-    assert len(proof_b) == 21 * 32 + 43 * 32 and h.verify_proof(vk, proof_b, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL)
+    assert len(proof_b) == 1920 and h.verify_proof(vk, proof_b, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
     with pytest.raises(ValueError):
         zkw.generate_proof_evm(x, y[:-1] + b"\xff", r, s, m, "./keys/proving_key.pk", 17)     # not on the curve / non-canonical
     with pytest.raises(ValueError):
@@ -131,8 +133,48 @@ def test_k19_proof_is_accepted(zkw, oracle):
     proof = st.prove(b"assertion-0", zkw.TRANSCRIPT_EVM, seed=1)
     assert len(proof) == 15 * 64 + 18 * 32
     assert h.verify_proof(vk, proof, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+    # Blake2b + SHPLONK at k = 19: 960 bytes, the reference's published proof size (ecdsa_bench.csv:2)
+    pb = st.prove(b"assertion-0", zkw.TRANSCRIPT_BLAKE2B, seed=2, shplonk=True)
+    assert len(pb) == 960 and h.verify_proof(vk, pb, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
     adv = st.synthesize(b"assertion-0")
     adv[0] = adv[0].copy()
     adv[0][3] = adv[0][7]      # break gate 0: d != a + b*c
     bad = zkw.create_proof(st.ctx, st.pk, adv, seed=1, transcript=zkw.TRANSCRIPT_EVM)
     assert not h.verify_proof(vk, bad, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+
+
+def test_prover_pool_batch(zkw, oracle):
+    """Independent assertions proven concurrently by several provers on one GPU: every proof verifies,
+    proofs for different assertions differ, and the same (assertion, seed) gives the same bytes on any worker."""
+    from oracle import halo2_ref as h
+    params = zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3)
+    pool = zkw.ProverPool(params, 0, workers=3)
+    try:
+        assertions = [b"assertion-%d" % i for i in range(8)] + [b"assertion-0"]
+        proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM, seed0=7)
+        assert len(set(proofs)) == len(proofs)   # last one repeats the assertion but not the seed
+        st = pool.states[0]
+        oshape = h.Shape(10, 2, 1, 1)
+        vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
+        for p in proofs:
+            assert h.verify_proof(vk, p, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+        again = [s.prove(b"assertion-3", zkw.TRANSCRIPT_EVM, seed=10) for s in pool.states]
+        assert again[0] == again[1] == again[2] == proofs[3]
+    finally:
+        pool.close()
+
+
+@pytest.mark.parametrize("degree,size", [(16, 3552), (15, 6560), (14, 12704)])
+def test_proof_sizes_match_reference_csv(zkw, oracle, degree, size):
+    """generate_proof (Blake2b + SHPLONK) for the wider configs of bench_ecdsa.config: the byte counts the
+    reference publishes in halo2-circuits/src/results/ecdsa_bench.csv:5-7, and the proofs verify."""
+    from oracle import halo2_ref as h
+    st = zkw.ProverState(zkw.CircuitParams.for_degree(degree), 0)
+    try:
+        p = st.params
+        proof = st.prove(b"assertion", zkw.TRANSCRIPT_BLAKE2B, seed=3, shplonk=True)
+        assert len(proof) == size
+        vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(degree, p.num_advice, p.num_lookup_advice, p.num_fixed))
+        assert h.verify_proof(vk, proof, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
+    finally:
+        st.close()

@@ -37,6 +37,32 @@ def test_round_trip(k, A, L, F, kind):
     assert not h.verify_proof(pk.vk, h.create_proof(pk, g, gl, wrong, seed=42, kind=kind), kind, tau=TAU)
 
 
+@pytest.mark.parametrize("k,A,L,F,kind", [(5, 1, 0, 1, "blake2b"), (6, 4, 1, 1, "blake2b"), (5, 2, 1, 2, "evm")])
+def test_round_trip_shplonk(k, A, L, F, kind):
+    shape = h.Shape(k, A, L, F)
+    fixed, mapping, advice = sc.build(shape, seed=k)
+    g, gl = dev_srs(shape)
+    pk = h.keygen(shape, gl, fixed, h.sigma_from_cycles(shape, mapping))
+    proof = h.create_proof(pk, g, gl, advice, seed=42, kind=kind, multiopen="shplonk")
+    assert h.verify_proof(pk.vk, proof, kind, tau=TAU, multiopen="shplonk")
+    assert not h.verify_proof(pk.vk, proof, kind, tau=TAU, multiopen="gwc")
+    for pos in (10, len(proof) // 2, len(proof) - 40, len(proof) - 1):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert not h.verify_proof(pk.vk, bytes(bad), kind, tau=TAU, multiopen="shplonk")
+    if (k, A, L, F, kind) == (5, 1, 0, 1, "blake2b"):
+        assert len(proof) == 960      # the k = 19 layout: halo2-circuits/src/results/ecdsa_bench.csv:2
+    if (k, A, L, F, kind) == (6, 4, 1, 1, "blake2b"):
+        assert len(proof) == 1920     # the k = 17 layout: ecdsa_bench.csv:4
+
+
+def test_lagrange_interpolate():
+    pts = [3, 7, 11, 20]
+    coeffs = [5, 0, 9, 2]
+    evals = [pr.poly_eval(coeffs, p) for p in pts]
+    assert h.lagrange_interpolate(pts, evals) == coeffs
+
+
 def test_proof_sizes_match_reference():
     """k=17 config under the EVM transcript: 2720 bytes = the golden proof's length
     (contracts/test/P256Account.t.sol:120).  k=19 config under Blake2b: 10 + 5 (GWC) commitments and 18

@@ -453,7 +453,7 @@ int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advi
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
                         int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!ctx || !pk || !advice || !advice_rows || !out_len || (transcript != 0 && transcript != 1)) return ZKW_ERR_INVALID;
-    const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL;
+    const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL, shplonk = flags & ZKW_MULTIOPEN_SHPLONK;
     ZKW_CUDA(ctx, cudaSetDevice(ctx->device));
     const zkw_circuit_shape& sh = pk->shape;
     const size_t n = pk->n, en = pk->en, u = pk->u, vb = n * 32, eb = en * 32;
@@ -667,40 +667,30 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     std::vector<int> rots;
     for (auto& q : queries) if (std::find(rots.begin(), rots.end(), q.rot) == rots.end()) rots.push_back(q.rot);
 
-    // batched evaluation of everything the proof carries: advice, fixed, random, sigma, perm z, lookups
-    struct EvalReq { const uint64_t* poly; int rot; };
-    std::vector<EvalReq> ev;
-    for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) ev.push_back({adv[c], r});
-    for (unsigned l = 0; l < L; l++) ev.push_back({adv[A + l], 0});
-    for (unsigned c = 0; c < pk->nfixed; c++) ev.push_back({pk->fixed_polys[c], 0});
-    ev.push_back({random_poly, 0});
-    for (unsigned c = 0; c < pk->nperm; c++) ev.push_back({pk->sigma_polys[c], 0});
-    for (unsigned s = 0; s < nsets; s++) {
-        ev.push_back({perm_z[s], 0}); ev.push_back({perm_z[s], 1});
-        if (s + 1 != nsets) ev.push_back({perm_z[s], last_rot});
-    }
-    for (unsigned l = 0; l < nlk; l++) {
-        ev.push_back({lk_z[l], 0}); ev.push_back({lk_z[l], 1}); ev.push_back({lk_a[l], 0}); ev.push_back({lk_a[l], -1}); ev.push_back({lk_s[l], 0});
-    }
-    {
-        // power tables x_r^(2^l) per distinct rotation
-        std::vector<Fr> pows(rots.size() * 40);
-        for (size_t p = 0; p < rots.size(); p++) {
-            Fr v = rotate(dom, x, rots[p]);
-            for (int l = 0; l < 40; l++) { pows[p * 40 + l] = v; v = v.sqr(); }
+    // batched polynomial evaluation: (poly, point) pairs -> values, two reduction levels on the device
+    auto eval_many = [&](const std::vector<std::pair<const uint64_t*, Fr>>& reqs, std::vector<Fr>& vals) -> int {
+        Scratch es(ctx);
+        std::vector<Fr> pts;
+        std::vector<EvalJob> jobs(reqs.size());
+        for (size_t i = 0; i < reqs.size(); i++) {
+            size_t pi = 0;
+            while (pi < pts.size() && pts[pi] != reqs[i].second) pi++;
+            if (pi == pts.size()) pts.push_back(reqs[i].second);
+            jobs[i].coeffs = (const uint4*)reqs[i].first;
+            jobs[i].point = (uint32_t)pi;
         }
-        std::vector<EvalJob> jobs(ev.size());
-        for (size_t i = 0; i < ev.size(); i++) {
-            jobs[i].coeffs = (const uint4*)ev[i].poly;
-            jobs[i].point = (uint32_t)(std::find(rots.begin(), rots.end(), ev[i].rot) - rots.begin());
+        std::vector<Fr> pows(pts.size() * 40);
+        for (size_t pi = 0; pi < pts.size(); pi++) {
+            Fr w = pts[pi];
+            for (int l = 0; l < 40; l++) { pows[pi * 40 + l] = w; w = w.sqr(); }
         }
         uint64_t *d_pows, *d_part0, *d_part1;
         EvalJob* d_jobs;
         const size_t nb0 = (n + kScanBlock - 1) / kScanBlock, nb1 = (nb0 + kScanBlock - 1) / kScanBlock;
-        ZKW_TRY(sc.get(pows.size() * 32, (void**)&d_pows));
-        ZKW_TRY(sc.get(jobs.size() * sizeof(EvalJob), (void**)&d_jobs));
-        ZKW_TRY(sc.get(jobs.size() * nb0 * 32, (void**)&d_part0));
-        ZKW_TRY(sc.get(jobs.size() * nb1 * 32, (void**)&d_part1));
+        ZKW_TRY(es.get(pows.size() * 32, (void**)&d_pows));
+        ZKW_TRY(es.get(jobs.size() * sizeof(EvalJob), (void**)&d_jobs));
+        ZKW_TRY(es.get(jobs.size() * nb0 * 32, (void**)&d_part0));
+        ZKW_TRY(es.get(jobs.size() * nb1 * 32, (void**)&d_part1));
         ZKW_CUDA(ctx, cudaMemcpyAsync(d_pows, pows.data(), pows.size() * 32, cudaMemcpyHostToDevice, st));
         ZKW_CUDA(ctx, cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(EvalJob), cudaMemcpyHostToDevice, st));
         { ProfScope ps_(ctx, "eval_reduce_kernel"); eval_reduce_kernel<<<dim3((unsigned)nb0, (unsigned)jobs.size()), kScanThreads, 0, st>>>(d_jobs, nullptr, 0, (const uint4*)d_pows, 0, (uint4*)d_part0, n, nb0); }
@@ -719,19 +709,188 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             which ^= 1;
             log_stride += 11;
         }
-        std::vector<Fr> vals(jobs.size());
-        // results are strided by `stride` (== 1 here)
+        vals.resize(jobs.size());
         ZKW_CUDA(ctx, cudaMemcpy2DAsync(vals.data(), 32, result, stride * 32, 32, jobs.size(), cudaMemcpyDeviceToHost, st));
         ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+        return ZKW_OK;
+    };
+    // everything the proof carries: advice, fixed, random, sigma, perm z, lookups
+    {
+        std::vector<std::pair<const uint64_t*, Fr>> ev;
+        auto at = [&](const uint64_t* poly, int r) { ev.push_back({poly, rotate(dom, x, r)}); };
+        for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) at(adv[c], r);
+        for (unsigned l = 0; l < L; l++) at(adv[A + l], 0);
+        for (unsigned c = 0; c < pk->nfixed; c++) at(pk->fixed_polys[c], 0);
+        at(random_poly, 0);
+        for (unsigned c = 0; c < pk->nperm; c++) at(pk->sigma_polys[c], 0);
+        for (unsigned s = 0; s < nsets; s++) {
+            at(perm_z[s], 0); at(perm_z[s], 1);
+            if (s + 1 != nsets) at(perm_z[s], last_rot);
+        }
+        for (unsigned l = 0; l < nlk; l++) { at(lk_z[l], 0); at(lk_z[l], 1); at(lk_a[l], 0); at(lk_a[l], -1); at(lk_s[l], 0); }
+        std::vector<Fr> vals;
+        ZKW_TRY(eval_many(ev, vals));
         for (auto& v : vals) tr.write_scalar(v);
+    }
+
+    // kate division of an n-coefficient polynomial by (X - z): q has n-1 coefficients, q[n-1] = 0
+    uint64_t *kd_terms, *kd_pre;
+    ZKW_TRY(sc.get(vb, (void**)&kd_terms));
+    ZKW_TRY(sc.get(vb, (void**)&kd_pre));
+    auto kate_div = [&](const uint64_t* poly, const Fr& z, uint64_t* q) -> int {
+        const Fr zinv = z.inv();
+        { ProfScope ps_(ctx, "kate_terms_kernel"); kate_terms_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)poly, (uint4*)kd_terms, z, n); }
+        ZKW_LAUNCHED(ctx);
+        ZKW_TRY((scan_run<false, false>(ctx, kd_terms, kd_pre, n, blocks, nullptr)));
+        ZKW_CUDA(ctx, cudaMemsetAsync(q + 4 * (n - 1), 0, 32, st));
+        { ProfScope ps_(ctx, "kate_finish_kernel"); kate_finish_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)kd_pre, (uint4*)q, zinv, n); }
+        ZKW_LAUNCHED(ctx);
+        return ZKW_OK;
+    };
+
+    if (shplonk) {
+        // ---- 8'. multi-open (SHPLONK): halo2_proofs::poly::kzg::multiopen::shplonk::ProverSHPLONK ----
+        const Fr ych = tr.squeeze();
+        const Fr vch = tr.squeeze();
+        auto canon_less = [](const Fr& a, const Fr& b) {
+            Fr ca = a.from_mont(), cb = b.from_mont();
+            for (int i = 7; i >= 0; i--) if (ca.l[i] != cb.l[i]) return ca.l[i] < cb.l[i];
+            return false;
+        };
+        // commitment -> point set (first-appearance order), then point set -> commitments
+        struct Comm { const uint64_t* poly; std::vector<Fr> pts; };
+        std::vector<Comm> comms;
+        std::vector<Fr> super_pts;
+        for (auto& q : queries) {
+            const Fr pt = rotate(dom, x, q.rot);
+            if (std::find(super_pts.begin(), super_pts.end(), pt) == super_pts.end()) super_pts.push_back(pt);
+            auto it = std::find_if(comms.begin(), comms.end(), [&](const Comm& c) { return c.poly == q.poly; });
+            if (it == comms.end()) comms.push_back({q.poly, {pt}});
+            else if (std::find(it->pts.begin(), it->pts.end(), pt) == it->pts.end()) it->pts.push_back(pt);
+        }
+        for (auto& c : comms) std::sort(c.pts.begin(), c.pts.end(), canon_less);   // BTreeSet order
+        struct RSet { std::vector<Fr> pts; std::vector<const uint64_t*> polys; std::vector<std::vector<Fr>> r_x; };
+        std::vector<RSet> rsets;
+        for (auto& c : comms) {
+            auto it = std::find_if(rsets.begin(), rsets.end(), [&](const RSet& r) { return r.pts == c.pts; });
+            if (it == rsets.end()) { rsets.push_back({c.pts, {c.poly}, {}}); }
+            else it->polys.push_back(c.poly);
+        }
+        // evaluations of every commitment at the points of its set, then the low-degree equivalents r(X)
+        {
+            std::vector<std::pair<const uint64_t*, Fr>> ev;
+            for (auto& rs : rsets) for (auto poly : rs.polys) for (auto& pt : rs.pts) ev.push_back({poly, pt});
+            std::vector<Fr> vals;
+            ZKW_TRY(eval_many(ev, vals));
+            size_t k = 0;
+            for (auto& rs : rsets) {
+                const size_t m = rs.pts.size();
+                for (size_t pi = 0; pi < rs.polys.size(); pi++) {
+                    // Lagrange interpolation through (pts[i], vals[k + i])
+                    std::vector<Fr> out(m, Fr::zero());
+                    for (size_t i = 0; i < m; i++) {
+                        std::vector<Fr> num(1, Fr::one());
+                        Fr den = Fr::one();
+                        for (size_t j = 0; j < m; j++) {
+                            if (j == i) continue;
+                            std::vector<Fr> nn(num.size() + 1, Fr::zero());
+                            for (size_t d = 0; d < num.size(); d++) { nn[d + 1] = nn[d + 1] + num[d]; nn[d] = nn[d] - rs.pts[j] * num[d]; }
+                            num.swap(nn);
+                            den = den * (rs.pts[i] - rs.pts[j]);
+                        }
+                        const Fr cf = vals[k + i] * den.inv();
+                        for (size_t d = 0; d < num.size(); d++) out[d] = out[d] + cf * num[d];
+                    }
+                    rs.r_x.push_back(out);
+                    k += m;
+                }
+            }
+        }
+        auto host_eval = [](const std::vector<Fr>& c, const Fr& at) { Fr acc = Fr::zero(); for (size_t i = c.size(); i-- > 0;) acc = acc * at + c[i]; return acc; };
+        uint64_t *tmp_a, *tmp_b, *h_x, *d_low;
+        ZKW_TRY(sc.get(vb, (void**)&tmp_a)); ZKW_TRY(sc.get(vb, (void**)&tmp_b)); ZKW_TRY(sc.get(vb, (void**)&h_x));
+        ZKW_TRY(sc.get(8 * 32, (void**)&d_low));
+        std::vector<uint64_t*> qsets(rsets.size());
+        for (size_t i = 0; i < rsets.size(); i++) {
+            RSet& rs = rsets[i];
+            // N_i(X) = sum_j y^j (P_ij(X) - r_ij(X))
+            std::vector<const uint64_t*> ps(rs.polys.begin(), rs.polys.end());
+            std::vector<Fr> ws;
+            std::vector<Fr> low(rs.pts.size(), Fr::zero());
+            Fr py = Fr::one();
+            for (size_t j = 0; j < rs.polys.size(); j++) {
+                ws.push_back(py);
+                for (size_t d = 0; d < low.size(); d++) low[d] = low[d] + py * rs.r_x[j][d];
+                py = py * ych;
+            }
+            ZKW_TRY(lincomb(ps, ws, tmp_a));
+            ZKW_CUDA(ctx, cudaMemcpyAsync(d_low, low.data(), low.size() * 32, cudaMemcpyHostToDevice, st));
+            { ProfScope ps_(ctx, "sub_low_kernel"); sub_low_kernel<<<1, 32, 0, st>>>((uint4*)tmp_a, (const uint4*)d_low, (int)low.size()); }
+            ZKW_LAUNCHED(ctx);
+            ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+            // Q_i = N_i / prod (X - p): successive synthetic divisions
+            ZKW_TRY(sc.get(vb, (void**)&qsets[i]));
+            uint64_t* src = tmp_a;
+            for (size_t pi = 0; pi < rs.pts.size(); pi++) {
+                uint64_t* dst = (pi + 1 == rs.pts.size()) ? qsets[i] : (src == tmp_a ? tmp_b : tmp_a);
+                ZKW_TRY(kate_div(src, rs.pts[pi], dst));
+                src = dst;
+            }
+        }
+        {
+            std::vector<const uint64_t*> ps(qsets.begin(), qsets.end());
+            std::vector<Fr> ws;
+            Fr pv = Fr::one();
+            for (size_t i = 0; i < rsets.size(); i++) { ws.push_back(pv); pv = pv * vch; }
+            ZKW_TRY(lincomb(ps, ws, h_x));
+        }
+        ZKW_TRY(commit_batch(ctx, tr, {{ZKW_BASES_G, h_x}}, n));
+        const Fr uch = tr.squeeze();
+        // L(X) = sum_i v^i z_i sum_j y^j (P_ij(X) - r_ij(u)) - Z_T(u) h(X), scaled by 1 / z_0
+        std::vector<Fr> zdiff(rsets.size());
+        for (size_t i = 0; i < rsets.size(); i++) {
+            Fr z = Fr::one();
+            for (auto& d : super_pts) if (std::find(rsets[i].pts.begin(), rsets[i].pts.end(), d) == rsets[i].pts.end()) z = z * (uch - d);
+            zdiff[i] = z;
+        }
+        Fr zt = Fr::one();
+        for (auto& d : super_pts) zt = zt * (uch - d);
+        const Fr inv0 = zdiff[0].inv();
+        std::vector<const uint64_t*> ps;
+        std::vector<Fr> ws;
+        Fr cst = Fr::zero();
+        Fr pv = Fr::one();
+        for (size_t i = 0; i < rsets.size(); i++) {
+            Fr py = Fr::one();
+            const Fr wi = pv * zdiff[i] * inv0;
+            for (size_t j = 0; j < rsets[i].polys.size(); j++) {
+                ps.push_back(rsets[i].polys[j]);
+                ws.push_back(wi * py);
+                cst = cst + wi * py * host_eval(rsets[i].r_x[j], uch);
+                py = py * ych;
+            }
+            pv = pv * vch;
+        }
+        ps.push_back(h_x);
+        ws.push_back((zt * inv0).neg());
+        ZKW_TRY(lincomb(ps, ws, tmp_a));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(d_low, cst.l, 32, cudaMemcpyHostToDevice, st));
+        { ProfScope ps_(ctx, "sub_low_kernel"); sub_low_kernel<<<1, 32, 0, st>>>((uint4*)tmp_a, (const uint4*)d_low, 1); }
+        ZKW_LAUNCHED(ctx);
+        ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+        ZKW_TRY(kate_div(tmp_a, uch, tmp_b));
+        ZKW_TRY(commit_batch(ctx, tr, {{ZKW_BASES_G, tmp_b}}, n));
+        *out_len = tr.out.size();
+        if (!out || out_cap < tr.out.size()) return ZKW_ERR_INVALID;
+        memcpy(out, tr.out.data(), tr.out.size());
+        return ZKW_OK;
     }
 
     // ---- 8. multi-open (GWC) ----
     const Fr v = tr.squeeze();
     {
-        uint64_t *batch, *terms, *pre;
-        ZKW_TRY(sc.get(vb, (void**)&batch)); ZKW_TRY(sc.get(vb, (void**)&terms));
-        ZKW_TRY(sc.get(vb, (void**)&pre));
+        uint64_t* batch;
+        ZKW_TRY(sc.get(vb, (void**)&batch));
         std::vector<std::pair<int, const uint64_t*>> wpolys;
         for (int r : rots) {
             uint64_t* wit;
@@ -741,14 +900,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             Fr pv = Fr::one();
             for (auto& q : queries) if (q.rot == r) { ps.push_back(q.poly); ws.push_back(pv); pv = pv * v; }
             ZKW_TRY(lincomb(ps, ws, batch));
-            const Fr z = rotate(dom, x, r);
-            const Fr zinv = z.inv();
-            { ProfScope ps_(ctx, "kate_terms_kernel"); kate_terms_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)batch, (uint4*)terms, z, n); }
-            ZKW_LAUNCHED(ctx);
-            ZKW_TRY((scan_run<false, false>(ctx, terms, pre, n, blocks, nullptr)));
-            ZKW_CUDA(ctx, cudaMemsetAsync(wit + 4 * (n - 1), 0, 32, st));
-            { ProfScope ps_(ctx, "kate_finish_kernel"); kate_finish_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)pre, (uint4*)wit, zinv, n); }
-            ZKW_LAUNCHED(ctx);
+            ZKW_TRY(kate_div(batch, rotate(dom, x, r), wit));
             wpolys.push_back({ZKW_BASES_G, wit});
         }
         ZKW_TRY(commit_batch(ctx, tr, wpolys, n));

@@ -406,6 +406,13 @@ __global__ void __launch_bounds__(128) lincomb_kernel(const LinCombArgs a, uint4
     acc.store(out + 2 * i);
 }
 
+// poly[d] -= low[d] for d < m (m <= 8): subtracting a low-degree polynomial
+__global__ void sub_low_kernel(uint4* poly, const uint4* low, int m) {
+    const int d = threadIdx.x;
+    if (d >= m) return;
+    (Fr::load(poly + 2 * d) - Fr::load(low + 2 * d)).store(poly + 2 * d);
+}
+
 // ---- (p(X) - p(z)) / (X - z) --------------------------------------------------------------------------------
 // q_{i-1} = sum_{j >= i} a_j z^(j-i) = z^-i (p(z) - sum_{j<i} a_j z^j).  Step 1: t_j = a_j z^j.
 // Step 2: additive prefix scan of t (scan_*<false,false>).  Step 3: q_{i-1} = z^-i (E - PRE_{i-1}),

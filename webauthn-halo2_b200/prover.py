@@ -93,17 +93,18 @@ def keygen(ctx: native.Context, shape: native.CircuitShape, fixed_values: list[n
     return ProvingKey(ctx, h, shape, circuit)
 
 
-ADVICE_ON_DEVICE, ADVICE_CANONICAL = 1, 2
+ADVICE_ON_DEVICE, ADVICE_CANONICAL, MULTIOPEN_SHPLONK = 1, 2, 4
 _PROOF_CAP = 1 << 20
 
 
 def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, transcript: int, *, canonical: bool = False,
-                 device_rows: list[int] | None = None) -> bytes:
+                 device_rows: list[int] | None = None, shplonk: bool = False) -> bytes:
     """create_proof on the device.  advice: one (rows, 4) uint64 array per advice column — host numpy arrays,
     or (with device_rows given) device tensors / addresses.  canonical=True: values are plain integers that
-    the device converts to Montgomery form."""
+    the device converts to Montgomery form.  shplonk=True: SHPLONK multi-open (the reference's generate_proof)
+    instead of GWC (generate_proof_evm)."""
     _bind(ctx.lib)
-    flags = ADVICE_CANONICAL if canonical else 0
+    flags = (ADVICE_CANONICAL if canonical else 0) | (MULTIOPEN_SHPLONK if shplonk else 0)
     if device_rows is not None:
         flags |= ADVICE_ON_DEVICE
         at = (u64p * len(advice))(*[C.cast(native._addr(a), u64p) for a in advice])
@@ -139,12 +140,12 @@ class ProverState:
     def synthesize(self, assertion: bytes) -> list[np.ndarray]:
         return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
 
-    def prove(self, assertion: bytes, transcript: int, seed: int | None = None) -> bytes:
+    def prove(self, assertion: bytes, transcript: int, seed: int | None = None, shplonk: bool = False) -> bytes:
         """witness synthesis on the host, one H2D copy of the canonical advice values, proof bytes back."""
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
         cols = [to_limbs(c) for c in self.circuit.synthesize(assertion)]
-        return create_proof(self.ctx, self.pk, cols, seed, transcript, canonical=True)
+        return create_proof(self.ctx, self.pk, cols, seed, transcript, canonical=True, shplonk=shplonk)
 
     def close(self):
         self.pk.close()
@@ -226,9 +227,9 @@ def _assertion_bytes(pubkey_x, pubkey_y, r, s, msg_hash) -> bytes:
 
 def generate_proof(pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg_hash: bytes, proving_key_path: str, degree: int,
                    device: int = 0, seed: int | None = None) -> bytes:
-    """ecdsa_p256.rs:379-427 — Blake2b transcript."""
+    """ecdsa_p256.rs:379-427 — Blake2b transcript, SHPLONK multi-open."""
     a = _assertion_bytes(pubkey_x, pubkey_y, r, s, msg_hash)
-    return download_keys(degree, proving_key_path, None, device).prove(a, TRANSCRIPT_BLAKE2B, seed)
+    return download_keys(degree, proving_key_path, None, device).prove(a, TRANSCRIPT_BLAKE2B, seed, shplonk=True)
 
 
 def generate_proof_evm(pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg_hash: bytes, proving_key_path: str, degree: int,
