@@ -107,7 +107,7 @@ def test_msm_before_srs_load_is_an_error(zkw, oracle):
         c.close()
 
 
-@pytest.mark.parametrize("c_bits", [4, 7, 11, 13, 16])
+@pytest.mark.parametrize("c_bits", [4, 7, 11, 13, 16, 19, 20])
 def test_msm_window_sizes(zkw, oracle, c_bits):
     c = zkw.Context(0)
     try:

@@ -373,6 +373,10 @@ int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint
 
 static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
     if (ctx->msm_window_bits > 0) return ctx->msm_window_bits;
+    // larger windows pay off once the bucket-side work (~2^(c-1) * c / 2 additions) is small against the
+    // N * ceil(255 / c) mixed additions of the accumulation
+    if (n >= (1u << 22)) return 20;
+    if (n >= (1u << 21)) return 19;
     return n >= (1u << 13) ? 16 : 8;
 }
 
