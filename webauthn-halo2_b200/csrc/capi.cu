@@ -110,6 +110,7 @@ static void profile_collect(zkw_ctx* ctx) {
     if (ctx->prof_pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
     for (int i = 1; i < zkw_ctx::kMsmLanes; i++) if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     for (auto& r : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
@@ -218,7 +219,10 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->twiddles) free_buffer(kv.second);
-    free_buffer(ctx->ntt_scratch); free_buffer(ctx->msm_ws);
+    free_buffer(ctx->ntt_scratch); free_buffer(ctx->ntt_scratch_aux); free_buffer(ctx->msm_ws);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
+    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table); free_buffer(ctx->arena);
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -51,7 +51,9 @@ struct zkw_ctx {
     // twiddle tables: omega^i for i < 2^(log_n-1), keyed by (omega, log_n)
     std::map<zkw::TwiddleKey, zkw::DeviceBuffer> twiddles;
     // reusable scratch areas (grown on demand, never shrunk)
-    zkw::DeviceBuffer ntt_scratch;
+    zkw::DeviceBuffer ntt_scratch, ntt_scratch_aux;
+    cudaStream_t aux_stream = nullptr;   // prover: transforms that overlap the main stream's MSMs
+    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
     zkw::DeviceBuffer msm_ws;
     // MSM lanes: lane 0 runs on `stream`; lanes 1.. own a side stream so that the latency-bound tails of
     // one MSM overlap the accumulation of the next (msm_run_batch)
@@ -118,13 +120,18 @@ int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, cons
 // generic transform: dst (2^log_n) <- NTT_omega(src'), src' = src zero-extended from 2^src_log_n with
 // optional zeta^(i mod 3) pre-scaling (coset) ; optional per-(i mod 3) output scaling. src may equal dst.
 int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t* dst_dev, unsigned log_n,
-            const uint64_t omega[4], bool coset_in, const uint64_t* scale3 /* 3*4 u64 host, or NULL */);
+            const uint64_t omega[4], bool coset_in, const uint64_t* scale3 /* 3*4 u64 host, or NULL */,
+            cudaStream_t stream = nullptr /* default: the ctx stream */);
 // msm.cu
 int msm_run(zkw_ctx* ctx, int which_bases, const uint64_t* bases_dev, const uint64_t* scalars_dev, size_t n,
             uint64_t out_xyz_host[12]);
 struct MsmJob { int which_bases; const uint64_t* bases_dev; const uint64_t* scalars_dev; size_t n; };
 // up to zkw_ctx::kMsmLanes independent MSMs in flight at once; outs[i] = 12 u64 (x, y, 1) or Z = 0
 int msm_run_batch(zkw_ctx* ctx, const MsmJob* jobs, int count, uint64_t (*outs)[12]);
+// pipelined form: submit one MSM to a side lane (1 <= lane < kMsmLanes) as soon as its scalars are queued
+// on the main stream, keep working on the main stream, and collect later (synchronises)
+int msm_lane_submit(zkw_ctx* ctx, int lane, const MsmJob& job);
+int msm_lanes_collect(zkw_ctx* ctx, const int* lanes, int count, uint64_t (*outs)[12]);
 int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
 void msm_free_basis(MsmBasis& b);
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);

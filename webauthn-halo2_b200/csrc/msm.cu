@@ -575,4 +575,22 @@ int msm_run_batch(zkw_ctx* ctx, const MsmJob* jobs, int count, uint64_t (*outs)[
     return ZKW_OK;
 }
 
+int msm_lane_submit(zkw_ctx* ctx, int lane, const MsmJob& job) {
+    if (lane < 1 || lane >= zkw_ctx::kMsmLanes) return ZKW_ERR_INVALID;
+    ZKW_TRY(lane_init(ctx, 0));
+    ZKW_TRY(lane_init(ctx, lane));
+    ZKW_CUDA(ctx, cudaEventRecord(ctx->fork_event, ctx->stream));
+    ZKW_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[lane], ctx->fork_event, 0));
+    ZKW_TRY(msm_enqueue(ctx, lane, job.which_bases, job.bases_dev, job.scalars_dev, job.n));
+    ZKW_CUDA(ctx, cudaEventRecord(ctx->lane_done[lane], ctx->lane_stream[lane]));
+    return ZKW_OK;
+}
+
+int msm_lanes_collect(zkw_ctx* ctx, const int* lanes, int count, uint64_t (*outs)[12]) {
+    for (int i = 0; i < count; i++) ZKW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->lane_done[lanes[i]], 0));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < count; i++) msm_collect(ctx, lanes[i], outs[i]);
+    return ZKW_OK;
+}
+
 }  // namespace zkw

@@ -203,13 +203,17 @@ int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, cons
 }
 
 int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t* dst_dev, unsigned log_n,
-            const uint64_t omega[4], bool coset_in, const uint64_t* scale3) {
+            const uint64_t omega[4], bool coset_in, const uint64_t* scale3, cudaStream_t stream) {
+    // work on the auxiliary stream gets its own scratch so that it may overlap main-stream transforms
+    const bool aux = stream && stream != ctx->stream;
+    cudaStream_t st = stream ? stream : ctx->stream;
+    DeviceBuffer& scratch = aux ? ctx->ntt_scratch_aux : ctx->ntt_scratch;
     if (log_n > 28 || src_log_n > log_n) return ZKW_ERR_INVALID;
     const size_t n = (size_t)1 << log_n;
     if (log_n == 0) {
         Fr s0 = Fr::one(), s1 = s0, s2 = s0;
         if (scale3) { s0 = fr_from_host(scale3); s1 = fr_from_host(scale3 + 4); s2 = fr_from_host(scale3 + 8); }
-        { ProfScope ps_(ctx, "scale_kernel"); scale_kernel<<<1, 32, 0, ctx->stream>>>((const uint4*)src_dev, (uint4*)dst_dev, 1, s0, s1, s2, scale3 != nullptr); }
+        { ProfScope ps_(ctx, "scale_kernel", st); scale_kernel<<<1, 32, 0, st>>>((const uint4*)src_dev, (uint4*)dst_dev, 1, s0, s1, s2, scale3 != nullptr); }
         ZKW_LAUNCHED(ctx);
         return ZKW_OK;
     }
@@ -222,8 +226,8 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     const bool in_place = (const void*)src_dev == (const void*)dst_dev;
     uint64_t* tmp = nullptr;
     if (in_place && log_n > (unsigned)kTileLog) {
-        ZKW_TRY(ensure_buffer(ctx, ctx->ntt_scratch, n * 32));
-        tmp = (uint64_t*)ctx->ntt_scratch.ptr;
+        ZKW_TRY(ensure_buffer(ctx, scratch, n * 32));
+        tmp = (uint64_t*)scratch.ptr;
     }
     // single-tile transforms gather the whole input before the first barrier, so in place is safe
     NttPassArgs a;
@@ -259,13 +263,13 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         a.src = (const uint4*)cur_src;
         a.dst = (uint4*)out;
         const unsigned tiles = (unsigned)(n >> a.tl);
-        { ProfScope ps_(ctx, "ntt_pass_kernel"); ntt_pass_kernel<<<tiles, kNttThreads, 0, ctx->stream>>>(a); }
+        { ProfScope ps_(ctx, "ntt_pass_kernel", st); ntt_pass_kernel<<<tiles, kNttThreads, 0, st>>>(a); }
         ZKW_LAUNCHED(ctx);
         cur_src = out;
         s0 += B;
     }
     if ((const void*)cur_src != (const void*)dst_dev) {
-        ZKW_CUDA(ctx, cudaMemcpyAsync(dst_dev, cur_src, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(dst_dev, cur_src, n * 32, cudaMemcpyDeviceToDevice, st));
     }
     return ZKW_OK;
 }

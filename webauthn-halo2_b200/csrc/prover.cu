@@ -140,6 +140,8 @@ struct Scratch {
     explicit Scratch(zkw_ctx* c) : ctx(c), mark_off(c->arena_off), mark_virtual(c->arena_virtual) {}
     ~Scratch() {
         cudaStreamSynchronize(ctx->stream);
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+        for (int i = 1; i < zkw_ctx::kMsmLanes; i++) if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
         for (void* p : extra) cudaFree(p);
         ctx->arena_off = mark_off;
         ctx->arena_virtual = mark_virtual;
@@ -196,6 +198,38 @@ static int commit_batch(zkw_ctx* ctx, Transcript& tr, const std::vector<std::pai
     }
     return ZKW_OK;
 }
+
+// Pipelined commitments: each polynomial's MSM is submitted to a side lane the moment the polynomial is
+// queued on the main stream, which keeps producing the next one; flush() collects in submission order.
+struct LanePipe {
+    zkw_ctx* ctx;
+    Transcript& tr;
+    size_t n;
+    std::vector<int> lanes;
+    LanePipe(zkw_ctx* c, Transcript& t, size_t n_) : ctx(c), tr(t), n(n_) {}
+    int submit(int which, const uint64_t* poly) {
+        if ((int)lanes.size() == zkw_ctx::kMsmLanes - 1) ZKW_TRY(flush());
+        const int lane = 1 + (int)lanes.size();
+        ZKW_TRY(msm_lane_submit(ctx, lane, MsmJob{which, nullptr, poly, n}));
+        lanes.push_back(lane);
+        return ZKW_OK;
+    }
+    int flush() {
+        if (lanes.empty()) return ZKW_OK;
+        std::vector<std::array<uint64_t, 12>> outs(lanes.size());
+        ZKW_TRY(msm_lanes_collect(ctx, lanes.data(), (int)lanes.size(), reinterpret_cast<uint64_t(*)[12]>(outs.data())));
+        for (auto& o : outs) {
+            uint64_t xy[8];
+            memcpy(xy, o.data(), 64);
+            bool ident = true;
+            for (int i = 8; i < 12; i++) ident = ident && o[i] == 0;
+            if (ident) memset(xy, 0, 64);
+            tr.write_point(xy);
+        }
+        lanes.clear();
+        return ZKW_OK;
+    }
+};
 
 // inclusive scan of x (n elements) into out; MUL / REVERSE as in prover_kernels.cuh; tmp holds block totals
 template <bool MUL, bool REVERSE>
@@ -466,7 +500,30 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     Scratch sc(ctx);
     Transcript tr(transcript);
     tr.common_scalar(fr_of(pk->digest));
-    uint64_t pt[8];
+
+    // Auxiliary stream: as soon as a committed column is final, its coefficient form (iNTT) and extended
+    // coset (zeta-coset NTT) are computed there, overlapping the commitments running on the main stream
+    // and the MSM lanes.  The main stream joins before the quotient kernel.
+    if (!ctx->aux_stream) {
+        ZKW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+        ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+    }
+    cudaStream_t sx = ctx->aux_stream;
+    auto spawn_transform = [&](const uint64_t* lagrange, uint64_t** coeff_out, const uint64_t** ext_out) -> int {
+        uint64_t *cf, *ex;
+        ZKW_TRY(sc.get(vb, (void**)&cf));
+        ZKW_TRY(sc.get(eb, (void**)&ex));
+        ZKW_CUDA(ctx, cudaEventRecord(ctx->aux_fork, st));
+        ZKW_CUDA(ctx, cudaStreamWaitEvent(sx, ctx->aux_fork, 0));
+        ZKW_TRY(ntt_run(ctx, lagrange, sh.k, cf, sh.k, dom.dc.omega_inv, false, dom.dc.n_scale3, sx));
+        ZKW_TRY(ntt_run(ctx, cf, sh.k, ex, sh.ext_k, dom.dc.ext_omega, true, nullptr, sx));
+        *coeff_out = cf;
+        *ext_out = ex;
+        return ZKW_OK;
+    };
+    std::vector<uint64_t*> adv_cf(NA), perm_z_cf(nsets), lk_z_cf(nlk), lk_a_cf(nlk), lk_s_cf(nlk);
+    std::vector<const uint64_t*> e_adv(NA), e_pz(nsets), e_lz(nlk), e_la(nlk), e_ls(nlk);
 
     // ---- 1. advice ----
     std::vector<uint64_t*> adv(NA);
@@ -484,6 +541,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_LAUNCHED(ctx);
         }
         ZKW_TRY(rand_fill(ctx, adv[c] + 4 * u, n - u, seed, 1 + c, 0));
+        ZKW_TRY(spawn_transform(adv[c], &adv_cf[c], &e_adv[c]));
     }
     {
         std::vector<std::pair<int, const uint64_t*>> polys;
@@ -528,6 +586,8 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_LAUNCHED(ctx);
             ZKW_TRY(rand_fill(ctx, lk_a[l] + 4 * u, n - u, seed, 1000 + 2 * l, 0));
             ZKW_TRY(rand_fill(ctx, lk_s[l] + 4 * u, n - u, seed, 1001 + 2 * l, 0));
+            ZKW_TRY(spawn_transform(lk_a[l], &lk_a_cf[l], &e_la[l]));
+            ZKW_TRY(spawn_transform(lk_s[l], &lk_s_cf[l], &e_ls[l]));
         }
         std::vector<std::pair<int, const uint64_t*>> polys;
         for (unsigned l = 0; l < nlk; l++) { polys.push_back({ZKW_BASES_G_LAGRANGE, lk_a[l]}); polys.push_back({ZKW_BASES_G_LAGRANGE, lk_s[l]}); }
@@ -538,6 +598,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
 
     // ---- 3. permutation grand products ----
     std::vector<uint64_t*> perm_z(nsets);
+    LanePipe zpipe(ctx, tr, n);
     {
         const Fr delta = fr_of(kDeltaM);
         Fr dpow = Fr::one();
@@ -558,6 +619,8 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_LAUNCHED(ctx);
             const uint64_t* z0 = s ? perm_z[s - 1] + 4 * u : nullptr;
             ZKW_TRY(grand_product(ctx, num, den, pn, sd, blocks, total_dev, z0, perm_z[s], u, n, seed, 2000 + s));
+            ZKW_TRY(zpipe.submit(ZKW_BASES_G_LAGRANGE, perm_z[s]));
+            ZKW_TRY(spawn_transform(perm_z[s], &perm_z_cf[s], &e_pz[s]));
         }
     }
     // ---- 4. lookup grand products ----
@@ -565,40 +628,25 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         { ProfScope ps_(ctx, "lookup_numden_kernel"); lookup_numden_kernel<<<grid_for(n, 128), 128, 0, st>>>((const uint4*)lk_inp[l], (const uint4*)pk->fixed_values[pk->table_col()], (const uint4*)lk_a[l], (const uint4*)lk_s[l], beta, gamma, (uint4*)num, (uint4*)den, n); }
         ZKW_LAUNCHED(ctx);
         ZKW_TRY(grand_product(ctx, num, den, pn, sd, blocks, total_dev, nullptr, lk_z[l], u, n, seed, 3000 + l));
+        ZKW_TRY(zpipe.submit(ZKW_BASES_G_LAGRANGE, lk_z[l]));
+        ZKW_TRY(spawn_transform(lk_z[l], &lk_z_cf[l], &e_lz[l]));
     }
     // ---- 5. vanishing argument: random polynomial; commitments of this round in one batch ----
     uint64_t* random_poly;
     ZKW_TRY(sc.get(vb, (void**)&random_poly));
     ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
-    {
-        std::vector<std::pair<int, const uint64_t*>> polys;
-        for (unsigned s = 0; s < nsets; s++) polys.push_back({ZKW_BASES_G_LAGRANGE, perm_z[s]});
-        for (unsigned l = 0; l < nlk; l++) polys.push_back({ZKW_BASES_G_LAGRANGE, lk_z[l]});
-        polys.push_back({ZKW_BASES_G, random_poly});
-        ZKW_TRY(commit_batch(ctx, tr, polys, n));
-    }
+    ZKW_TRY(zpipe.submit(ZKW_BASES_G, random_poly));
+    ZKW_TRY(zpipe.flush());
     const Fr y = tr.squeeze();
 
     // ---- 6. quotient ----
-    // every committed column goes to coefficient form in place (the Lagrange values are no longer needed)
-    auto to_coeff = [&](uint64_t* v) { return ntt_run(ctx, v, sh.k, v, sh.k, dom.dc.omega_inv, false, dom.dc.n_scale3); };
-    for (auto v : adv) ZKW_TRY(to_coeff(v));
-    for (auto v : perm_z) ZKW_TRY(to_coeff(v));
-    for (unsigned l = 0; l < nlk; l++) { ZKW_TRY(to_coeff(lk_z[l])); ZKW_TRY(to_coeff(lk_a[l])); ZKW_TRY(to_coeff(lk_s[l])); }
+    // the coefficient forms and extended cosets were produced on the auxiliary stream: join it
+    ZKW_CUDA(ctx, cudaEventRecord(ctx->aux_join, sx));
+    ZKW_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_join, 0));
     uint64_t* h_ext;
     ZKW_TRY(sc.get(eb, (void**)&h_ext));
     {
-        Scratch ext(ctx);
-        auto to_ext = [&](const uint64_t* poly, const uint64_t** out_ext) -> int {
-            uint64_t* e;
-            ZKW_TRY(ext.get(eb, (void**)&e));
-            *out_ext = e;
-            return ntt_run(ctx, poly, sh.k, e, sh.ext_k, dom.dc.ext_omega, true, nullptr);
-        };
-        std::vector<const uint64_t*> e_adv(NA), e_pz(nsets), e_lz(nlk), e_la(nlk), e_ls(nlk), e_const(F), e_q(A), e_sig(pk->nperm);
-        for (unsigned c = 0; c < NA; c++) ZKW_TRY(to_ext(adv[c], &e_adv[c]));
-        for (unsigned s = 0; s < nsets; s++) ZKW_TRY(to_ext(perm_z[s], &e_pz[s]));
-        for (unsigned l = 0; l < nlk; l++) { ZKW_TRY(to_ext(lk_z[l], &e_lz[l])); ZKW_TRY(to_ext(lk_a[l], &e_la[l])); ZKW_TRY(to_ext(lk_s[l], &e_ls[l])); }
+        std::vector<const uint64_t*> e_const(F), e_q(A), e_sig(pk->nperm);
         for (unsigned c = 0; c < F; c++) e_const[c] = pk->fixed_cosets[c];
         for (unsigned c = 0; c < A; c++) e_q[c] = pk->fixed_cosets[pk->q_enable_col(c)];
         for (unsigned c = 0; c < pk->nperm; c++) e_sig[c] = pk->sigma_cosets[c];
@@ -611,8 +659,6 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         qi.l0 = pk->l0_coset; qi.l_last = pk->l_last_coset; qi.l_active = pk->l_active_coset;
         memcpy(qi.y, y.l, 32); memcpy(qi.beta, beta.l, 32); memcpy(qi.gamma, gamma.l, 32); memcpy(qi.theta, theta.l, 32);
         ZKW_TRY(quotient_run(ctx, &qi, h_ext));
-        DomainConsts dce;
-        domain_consts(sh.ext_k, sh.ext_k, &dce);
         ZKW_TRY(ntt_run(ctx, h_ext, sh.ext_k, h_ext, sh.ext_k, dom.dc.ext_omega_inv, false, dom.dc.ext_scale3));
     }
     const unsigned pieces = sh.cs_degree - 1;
@@ -628,13 +674,13 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     struct Query { int rot; const uint64_t* poly; };
     std::vector<Query> queries;
     const int last_rot = -((int)sh.blinding_factors + 1);
-    for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) queries.push_back({r, adv[c]});
-    for (unsigned l = 0; l < L; l++) queries.push_back({0, adv[A + l]});
-    for (unsigned s = 0; s < nsets; s++) { queries.push_back({0, perm_z[s]}); queries.push_back({1, perm_z[s]}); }
-    for (int s = (int)nsets - 2; s >= 0; s--) queries.push_back({last_rot, perm_z[s]});
+    for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) queries.push_back({r, adv_cf[c]});
+    for (unsigned l = 0; l < L; l++) queries.push_back({0, adv_cf[A + l]});
+    for (unsigned s = 0; s < nsets; s++) { queries.push_back({0, perm_z_cf[s]}); queries.push_back({1, perm_z_cf[s]}); }
+    for (int s = (int)nsets - 2; s >= 0; s--) queries.push_back({last_rot, perm_z_cf[s]});
     for (unsigned l = 0; l < nlk; l++) {
-        queries.push_back({0, lk_z[l]}); queries.push_back({0, lk_a[l]}); queries.push_back({0, lk_s[l]});
-        queries.push_back({-1, lk_a[l]}); queries.push_back({1, lk_z[l]});
+        queries.push_back({0, lk_z_cf[l]}); queries.push_back({0, lk_a_cf[l]}); queries.push_back({0, lk_s_cf[l]});
+        queries.push_back({-1, lk_a_cf[l]}); queries.push_back({1, lk_z_cf[l]});
     }
     for (unsigned c = 0; c < pk->nfixed; c++) queries.push_back({0, pk->fixed_polys[c]});
     for (unsigned c = 0; c < pk->nperm; c++) queries.push_back({0, pk->sigma_polys[c]});
@@ -718,16 +764,16 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     {
         std::vector<std::pair<const uint64_t*, Fr>> ev;
         auto at = [&](const uint64_t* poly, int r) { ev.push_back({poly, rotate(dom, x, r)}); };
-        for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) at(adv[c], r);
-        for (unsigned l = 0; l < L; l++) at(adv[A + l], 0);
+        for (unsigned c = 0; c < A; c++) for (int r = 0; r < 4; r++) at(adv_cf[c], r);
+        for (unsigned l = 0; l < L; l++) at(adv_cf[A + l], 0);
         for (unsigned c = 0; c < pk->nfixed; c++) at(pk->fixed_polys[c], 0);
         at(random_poly, 0);
         for (unsigned c = 0; c < pk->nperm; c++) at(pk->sigma_polys[c], 0);
         for (unsigned s = 0; s < nsets; s++) {
-            at(perm_z[s], 0); at(perm_z[s], 1);
-            if (s + 1 != nsets) at(perm_z[s], last_rot);
+            at(perm_z_cf[s], 0); at(perm_z_cf[s], 1);
+            if (s + 1 != nsets) at(perm_z_cf[s], last_rot);
         }
-        for (unsigned l = 0; l < nlk; l++) { at(lk_z[l], 0); at(lk_z[l], 1); at(lk_a[l], 0); at(lk_a[l], -1); at(lk_s[l], 0); }
+        for (unsigned l = 0; l < nlk; l++) { at(lk_z_cf[l], 0); at(lk_z_cf[l], 1); at(lk_a_cf[l], 0); at(lk_a_cf[l], -1); at(lk_s_cf[l], 0); }
         std::vector<Fr> vals;
         ZKW_TRY(eval_many(ev, vals));
         for (auto& v : vals) tr.write_scalar(v);
@@ -891,7 +937,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     {
         uint64_t* batch;
         ZKW_TRY(sc.get(vb, (void**)&batch));
-        std::vector<std::pair<int, const uint64_t*>> wpolys;
+        LanePipe wpipe(ctx, tr, n);
         for (int r : rots) {
             uint64_t* wit;
             ZKW_TRY(sc.get(vb, (void**)&wit));
@@ -901,9 +947,9 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             for (auto& q : queries) if (q.rot == r) { ps.push_back(q.poly); ws.push_back(pv); pv = pv * v; }
             ZKW_TRY(lincomb(ps, ws, batch));
             ZKW_TRY(kate_div(batch, rotate(dom, x, r), wit));
-            wpolys.push_back({ZKW_BASES_G, wit});
+            ZKW_TRY(wpipe.submit(ZKW_BASES_G, wit));
         }
-        ZKW_TRY(commit_batch(ctx, tr, wpolys, n));
+        ZKW_TRY(wpipe.flush());
     }
     *out_len = tr.out.size();
     if (!out || out_cap < tr.out.size()) return ZKW_ERR_INVALID;
