@@ -237,7 +237,7 @@ class FullProof:
         self.dev_cols = [torch.from_numpy(c.view(np.int64)).to(torch.device("cuda", device)) for c in cols]
         self.step_no = 0
         self.proof = b""
-        self.h2d = sum(c.nbytes for c in cols)
+        self.h2d = sum(c.shape[0] * 8 for c in cols)      # the public API ships one u64 per advice row
 
     def step(self):
         """advice already in HBM (canonical integers); blinding seed changes every step."""

@@ -227,7 +227,8 @@ int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advi
 /* flags: the advice arrays live in device memory / hold canonical integers (< 2r, little-endian u64
  * limbs) that the device converts to Montgomery form; the multi-open argument is SHPLONK (what the
  * reference's generate_proof uses, ecdsa_p256.rs:416-423) instead of GWC (generate_proof_evm, :366-373). */
-enum { ZKW_ADVICE_ON_DEVICE = 1, ZKW_ADVICE_CANONICAL = 2, ZKW_MULTIOPEN_SHPLONK = 4 /* default: GWC */ };
+enum { ZKW_ADVICE_ON_DEVICE = 1, ZKW_ADVICE_CANONICAL = 2, ZKW_MULTIOPEN_SHPLONK = 4 /* default: GWC */,
+       ZKW_ADVICE_U64 = 8 /* advice arrays hold ONE u64 per row (values < 2^64), widened + Montgomerised on the device */ };
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
                         uint64_t seed, int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
 

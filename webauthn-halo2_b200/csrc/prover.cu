@@ -487,7 +487,8 @@ int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advi
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
                         int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!ctx || !pk || !advice || !advice_rows || !out_len || (transcript != 0 && transcript != 1)) return ZKW_ERR_INVALID;
-    const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL, shplonk = flags & ZKW_MULTIOPEN_SHPLONK;
+    const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL, shplonk = flags & ZKW_MULTIOPEN_SHPLONK,
+               adv_u64 = flags & ZKW_ADVICE_U64;
     ZKW_CUDA(ctx, cudaSetDevice(ctx->device));
     const zkw_circuit_shape& sh = pk->shape;
     const size_t n = pk->n, en = pk->en, u = pk->u, vb = n * 32, eb = en * 32;
@@ -529,7 +530,14 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     std::vector<uint64_t*> adv(NA);
     for (unsigned c = 0; c < NA; c++) {
         ZKW_TRY(sc.get(vb, (void**)&adv[c]));
-        if (advice_rows[c]) {
+        if (advice_rows[c] && adv_u64) {
+            // compact form: one u64 per row, staged next to the column and widened on the device
+            uint64_t* stage;
+            ZKW_TRY(sc.get(advice_rows[c] * 8, (void**)&stage));
+            ZKW_CUDA(ctx, cudaMemcpyAsync(stage, advice[c], advice_rows[c] * 8, adv_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+            { ProfScope ps_(ctx, "u64_to_mont_kernel"); u64_to_mont_kernel<<<grid_for(advice_rows[c], 128), 128, 0, st>>>(stage, (uint4*)adv[c], advice_rows[c]); }
+            ZKW_LAUNCHED(ctx);
+        } else if (advice_rows[c]) {
             ZKW_CUDA(ctx, cudaMemcpyAsync(adv[c], advice[c], advice_rows[c] * 32, adv_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
             if (adv_canonical) {
                 { ProfScope ps_(ctx, "to_mont_kernel"); to_mont_kernel<<<grid_for(advice_rows[c], 128), 128, 0, st>>>((uint4*)adv[c], advice_rows[c]); }

@@ -60,6 +60,17 @@ __global__ void to_mont_kernel(uint4* v, size_t count) {
     x.to_mont().store(v + 2 * i);
 }
 
+// one u64 per row -> Montgomery field elements (in and out must not overlap)
+__global__ void u64_to_mont_kernel(const uint64_t* in, uint4* out, size_t count) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint64_t v = in[i];
+    Fr x = Fr::zero();
+    x.l[0] = (uint32_t)v;
+    x.l[1] = (uint32_t)(v >> 32);
+    x.to_mont().store(out + 2 * i);
+}
+
 // out[i] = a[i] * b[i]
 __global__ void mul_vec_kernel(const uint4* a, const uint4* b, uint4* out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

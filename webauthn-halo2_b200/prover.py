@@ -93,25 +93,25 @@ def keygen(ctx: native.Context, shape: native.CircuitShape, fixed_values: list[n
     return ProvingKey(ctx, h, shape, circuit)
 
 
-ADVICE_ON_DEVICE, ADVICE_CANONICAL, MULTIOPEN_SHPLONK = 1, 2, 4
+ADVICE_ON_DEVICE, ADVICE_CANONICAL, MULTIOPEN_SHPLONK, ADVICE_U64 = 1, 2, 4, 8
 _PROOF_CAP = 1 << 20
 
 
 def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, transcript: int, *, canonical: bool = False,
-                 device_rows: list[int] | None = None, shplonk: bool = False) -> bytes:
+                 device_rows: list[int] | None = None, shplonk: bool = False, u64: bool = False) -> bytes:
     """create_proof on the device.  advice: one (rows, 4) uint64 array per advice column — host numpy arrays,
     or (with device_rows given) device tensors / addresses.  canonical=True: values are plain integers that
-    the device converts to Montgomery form.  shplonk=True: SHPLONK multi-open (the reference's generate_proof)
+    the device converts to Montgomery form; u64=True: one uint64 per row ((rows,) arrays), widened on the device.  shplonk=True: SHPLONK multi-open (the reference's generate_proof)
     instead of GWC (generate_proof_evm)."""
     _bind(ctx.lib)
-    flags = (ADVICE_CANONICAL if canonical else 0) | (MULTIOPEN_SHPLONK if shplonk else 0)
+    flags = (ADVICE_CANONICAL if canonical else 0) | (MULTIOPEN_SHPLONK if shplonk else 0) | (ADVICE_U64 if u64 else 0)
     if device_rows is not None:
         flags |= ADVICE_ON_DEVICE
         at = (u64p * len(advice))(*[C.cast(native._addr(a), u64p) for a in advice])
         rows = (C.c_size_t * len(advice))(*device_rows)
         keep = advice
     else:
-        keep = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in advice]
+        keep = [np.ascontiguousarray(a, dtype=np.uint64).reshape((-1,) if u64 else (-1, 4)) for a in advice]
         at = (u64p * len(keep))(*[a.ctypes.data_as(u64p) for a in keep])
         rows = (C.c_size_t * len(keep))(*[a.shape[0] for a in keep])
     buf = (C.c_uint8 * _PROOF_CAP)()
@@ -144,8 +144,8 @@ class ProverState:
         """witness synthesis on the host, one H2D copy of the canonical advice values, proof bytes back."""
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
-        cols = [to_limbs(c) for c in self.circuit.synthesize(assertion)]
-        return create_proof(self.ctx, self.pk, cols, seed, transcript, canonical=True, shplonk=shplonk)
+        cols = self.circuit.synthesize(assertion)          # canonical values < 2^64: shipped as one u64 per row
+        return create_proof(self.ctx, self.pk, cols, seed, transcript, shplonk=shplonk, u64=True)
 
     def close(self):
         self.pk.close()
