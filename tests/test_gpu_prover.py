@@ -178,3 +178,34 @@ def test_proof_sizes_match_reference_csv(zkw, oracle, degree, size):
         assert h.verify_proof(vk, proof, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
     finally:
         st.close()
+
+
+def test_prover_abi_error_paths(zkw, oracle):
+    """Bad arguments come back as status codes (never aborts): too many advice rows, an SRS of the wrong
+    size, an output buffer that is too small, a shape the quotient kernel was not built for."""
+    import ctypes as C
+    ctx = zkw.Context(0)
+    try:
+        params = zkw.CircuitParams("Simple", 6, 2, 1, 1, 4, 88, 3)
+        circ, shape, oshape, pk, fixed_c, mapping = _setup(zkw, oracle, ctx, params)
+        too_long = [np.zeros((1 << 6, 4), dtype=np.uint64) for _ in range(3)]
+        with pytest.raises(zkw.ZkwError) as ei:
+            zkw.create_proof(ctx, pk, too_long, seed=1, transcript=zkw.TRANSCRIPT_EVM)
+        assert ei.value.status == -3
+        with pytest.raises(zkw.ZkwError):
+            zkw.create_proof(ctx, pk, [np.zeros((4, 4), dtype=np.uint64)] * 3, seed=1, transcript=7)
+        # keygen against a resident SRS of another size
+        ctx.srs_setup(7, oracle.fr_to_mont([TAU])[0])
+        with pytest.raises(zkw.ZkwError) as ei:
+            zkw.create_proof(ctx, pk, [np.zeros((4, 4), dtype=np.uint64)] * 3, seed=1, transcript=zkw.TRANSCRIPT_EVM)
+        assert ei.value.status == -5
+        fixed_m = [oracle.fr_to_mont([int(x) for x in col]) for col in fixed_c]
+        with pytest.raises(zkw.ZkwError) as ei:
+            zkw.keygen(ctx, shape, fixed_m, mapping)
+        assert ei.value.status == -5
+        bad_shape = zkw.CircuitShape(6, 8, 2, 0, 1, 6, 5, 0)   # selector mode with two gate columns
+        with pytest.raises(zkw.ZkwError):
+            zkw.keygen(ctx, bad_shape, fixed_m, mapping)
+        pk.close()
+    finally:
+        ctx.close()

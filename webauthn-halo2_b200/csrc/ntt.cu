@@ -24,6 +24,9 @@ namespace zkw {
 constexpr int kTileLog = 10;
 constexpr int kNttThreads = 128;
 constexpr int kMaxPassBits = 7;
+#ifndef ZKW_NTT_MIN_BLOCKS
+#define ZKW_NTT_MIN_BLOCKS 4
+#endif
 
 struct NttPassArgs {
     const uint4* src;
@@ -95,7 +98,7 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
     }
 }
 
-__global__ void __launch_bounds__(kNttThreads) ntt_pass_kernel(const NttPassArgs a) {
+__global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kernel(const NttPassArgs a) {
     __shared__ uint4 slo[1 << kTileLog];
     __shared__ uint4 shi[1 << kTileLog];
     const unsigned tile = blockIdx.x;

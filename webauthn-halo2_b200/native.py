@@ -20,7 +20,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libzkw_b200.so")
+LIB_PATH = os.environ.get("ZKW_B200_LIB") or os.path.join(HERE, "libzkw_b200.so")   # override: A/B builds of the same ABI
 
 ZKW_OK = 0
 ZKW_ERR_NO_DEVICE = -1
