@@ -279,12 +279,20 @@ def cpu_hot_path(k: int, threads: int):
     return 1.0 / per_proof, sample, t
 
 
+def host_threads() -> int:
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1, so the OpenMP default is
+    not trustworthy: the CPU arm passes this count to the oracle's num_threads clauses explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import cpu
-    threads = cpu.max_threads()
+    threads = host_threads()
     vals = []
     sample = ""
     for i in range(args.warmup + args.steps):
@@ -473,8 +481,7 @@ def run_b200(args):
         cpu_val, cpu_sample, _ = (None, "skipped", None)
         cores = None
         if world == 1 and not args.no_cpu:
-            from oracle import cpu as cpu_oracle
-            cores = cpu_oracle.max_threads()
+            cores = host_threads()
             cpu_val, cpu_sample, _ = cpu_hot_path(args.k, cores)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
