@@ -30,7 +30,10 @@
 
 namespace zkw {
 
-constexpr int kSlice = 32;         // entries per accumulate thread
+#ifndef ZKW_MSM_SLICE
+#define ZKW_MSM_SLICE 32
+#endif
+constexpr int kSlice = ZKW_MSM_SLICE;         // entries per accumulate thread
 constexpr int kSlice2 = 16;        // slice sums per second-level combine thread
 constexpr int kReduceBlocks = 16;  // CTAs per (group, bit) in the bit-sliced reduction
 constexpr int kReduceThreads = 128;
