@@ -4,6 +4,7 @@
 // evaluate_h (call sites in the reference: halo2-circuits/src/ecc/ecdsa_p256.rs:259-260, 366-373,
 // 416-423, 555-562).  No CPU fallback lives here: every path ends in a kernel launch or an error.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include "common.cuh"
@@ -82,6 +83,15 @@ void domain_consts(unsigned k, unsigned ext_k, DomainConsts* out) {
     *out = d;
 }
 
+int stream_priority(int level) {
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); return 0; }
+    // numerically lower = more urgent; level 0 = background, 2 = most urgent
+    if (level <= 0) return least;
+    if (level >= 2) return greatest;
+    return (least + greatest) / 2;
+}
+
 // ---- per-kernel timing ---------------------------------------------------------------------------
 static cudaEvent_t take_event(zkw_ctx* ctx) {
     if (!ctx->event_pool.empty()) {
@@ -100,7 +110,7 @@ ProfScope::ProfScope(zkw_ctx* c, const char* name, cudaStream_t s) : ctx(c), str
     stop = take_event(c);
     if (!start || !stop) { stop = nullptr; return; }
     cudaEventRecord(start, stream);
-    c->prof_pending.push_back({name, start, stop});
+    c->prof_pending.push_back({name, start, stop, stream});
 }
 ProfScope::~ProfScope() {
     if (stop) cudaEventRecord(stop, stream);
@@ -111,18 +121,26 @@ static void profile_collect(zkw_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 1; i < zkw_ctx::kMsmLanes; i++) if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
     if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    // ZKW_TIMELINE=<file>: also append one "name,stream,start_ms,duration_ms" line per launch (start relative
+    // to the first launch profiled), which is enough to see what overlaps what without a system profiler
+    const char* tl_path = getenv("ZKW_TIMELINE");
+    FILE* tl = tl_path ? fopen(tl_path, "a") : nullptr;
+    if (tl && !ctx->prof_ref) ctx->prof_ref = ctx->prof_pending.front().start;
     for (auto& r : ctx->prof_pending) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
             auto& t = ctx->prof_totals[r.name];
             t.first += ms;
             t.second += 1;
+            float t0 = 0.f;
+            if (tl && cudaEventElapsedTime(&t0, ctx->prof_ref, r.start) == cudaSuccess) fprintf(tl, "%s,%p,%.4f,%.4f\n", r.name, (void*)r.stream, t0, ms);
         } else {
             cudaGetLastError();
         }
-        ctx->event_pool.push_back(r.start);
+        if (r.start != ctx->prof_ref) ctx->event_pool.push_back(r.start);  // the reference event stays alive
         ctx->event_pool.push_back(r.stop);
     }
+    if (tl) fclose(tl);
     ctx->prof_pending.clear();
 }
 
@@ -202,7 +220,10 @@ int zkw_ctx_create(int device, zkw_ctx** out) {
     zkw_ctx* ctx = new zkw_ctx();
     ctx->device = device;
     e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    // The main stream carries the short, latency-critical kernels between commitments (scans, divisions,
+    // lookups); the MSM lanes and the transform stream carry long throughput-bound grids.  Without priorities a
+    // one-CTA scan queued behind a 2000-CTA bucket accumulation waits for the whole grid.
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, zkw::stream_priority(2));
     if (e != cudaSuccess) { int rc = set_cuda_error(ctx, e, "ctx init"); delete ctx; return rc; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

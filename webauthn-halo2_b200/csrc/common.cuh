@@ -74,7 +74,8 @@ struct zkw_ctx {
 
     // optional per-kernel timing (CUDA events on the ctx stream), off by default
     bool profiling = false;
-    struct ProfRec { const char* name; cudaEvent_t start, stop; };
+    struct ProfRec { const char* name; cudaEvent_t start, stop; cudaStream_t stream; };
+    cudaEvent_t prof_ref = nullptr;      // timeline origin (ZKW_TIMELINE)
     std::vector<ProfRec> prof_pending;
     std::map<std::string, std::pair<double, uint64_t>> prof_totals;  // name -> (ms, launches)
     std::vector<cudaEvent_t> event_pool;
@@ -83,6 +84,7 @@ struct zkw_ctx {
 namespace zkw {
 
 int set_cuda_error(zkw_ctx* ctx, cudaError_t e, const char* what);
+int stream_priority(int level);  // 0 = background (MSM lanes), 1 = transforms, 2 = the context's main stream
 int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes);
 
 #define ZKW_CUDA(ctx, call)                                            \
@@ -132,6 +134,8 @@ int msm_run_batch(zkw_ctx* ctx, const MsmJob* jobs, int count, uint64_t (*outs)[
 // on the main stream, keep working on the main stream, and collect later (synchronises)
 int msm_lane_submit(zkw_ctx* ctx, int lane, const MsmJob& job);
 int msm_lanes_collect(zkw_ctx* ctx, const int* lanes, int count, uint64_t (*outs)[12]);
+// wait for ONE lane's MSM (host blocks on that lane's event only) and fetch its result
+int msm_lane_wait(zkw_ctx* ctx, int lane, uint64_t out_xyz[12]);
 int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
 void msm_free_basis(MsmBasis& b);
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);

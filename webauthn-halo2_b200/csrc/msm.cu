@@ -20,9 +20,9 @@
 //              uniform: zeros, bits, small limbs).
 //   combine    two levels: one thread folds up to kSlice2 slice sums; then one warp per bucket folds what
 //              is left (one copy for almost every bucket, a strided loop + shuffle tree for heavy ones).
-//   reduce     sum_b b * B_b  =  sum_j 2^j * S_j  with  S_j = sum of buckets whose index has bit j set:
-//              c independent tree sums, fully parallel; the final 2c-step Horner runs on the host
-//              in microseconds instead of as a latency-bound single-thread chain on the device.
+//   reduce     sum_b b * B_b by rows and columns of the bucket index (b - 1 = hi * 2^lb + lo): tree sums of
+//              every row and column, then two short bit-sliced weighted sums; the final ~2c-step Horner
+//              runs on the host in microseconds instead of as a latency-bound chain on the device.
 //
 // The kernels are integer-ALU bound: 96 algorithmic bytes per point against ~10 field products per
 // window per point.  DESIGN.md carries the roofline arithmetic.
@@ -35,8 +35,7 @@ namespace zkw {
 #endif
 constexpr int kSlice = ZKW_MSM_SLICE;         // entries per accumulate thread
 constexpr int kSlice2 = 16;        // slice sums per second-level combine thread
-constexpr int kReduceBlocks = 16;  // CTAs per (group, bit) in the bit-sliced reduction
-constexpr int kReduceThreads = 128;
+constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
 struct MsmPlan {
     int c;            // window bits
@@ -245,7 +244,8 @@ __global__ void __launch_bounds__(128) msm_combine2_kernel(const uint4* __restri
 
 // ---- combine, level 3: one warp per bucket folds whatever level-2 sums the bucket has -----------------
 // Almost every bucket has exactly one (copy) — only heavy buckets (skewed scalars: zeros, bits, tiny
-// digits of sorted lookup columns) reach the strided loop and the shuffle tree.
+// digits of sorted lookup columns) reach the strided loop and the shuffle tree (one shared instance of the
+// point addition: runtime-counted loop, operand from memory or from a shuffle).
 __global__ void __launch_bounds__(128) msm_combine3_kernel(const uint4* __restrict__ partials2, const uint32_t* __restrict__ slice2_start,
                                                            uint4* __restrict__ buckets, uint32_t total_buckets) {
     const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -261,62 +261,89 @@ __global__ void __launch_bounds__(128) msm_combine3_kernel(const uint4* __restri
         return;
     }
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t s = s0 + lane; s < s1; s += 32) {
-        G1Xyzz p = G1Xyzz::load(partials2 + 8 * (size_t)s);
-        acc.add(p);
-    }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        G1Xyzz o = shfl_xor_point(acc, m, 0xffffffffu);
-        if (lane < m) acc.add(o);
+    const int nload = (int)((s1 - s0 + 31) / 32);
+#pragma unroll 1
+    for (int it = 0; it < nload + 5; it++) {
+        G1Xyzz o = G1Xyzz::identity();
+        if (it < nload) {
+            const uint32_t s = s0 + (uint32_t)it * 32u + (uint32_t)lane;
+            if (s < s1) o = G1Xyzz::load(partials2 + 8 * (size_t)s);
+        } else {
+            o = shfl_xor_point(acc, 16 >> (it - nload), 0xffffffffu);
+        }
+        acc.add(o);
     }
     if (lane == 0) acc.store(buckets + 8 * (size_t)b);
 }
 
-// ---- bit-sliced reduction: S[g][j] = sum over buckets of group g whose (index+1) has bit j ------------
-__global__ void __launch_bounds__(kReduceThreads) msm_bitreduce_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ block_out,
-                                                                       uint32_t nb, int c) {
-    __shared__ uint4 sh[(kReduceThreads / 32) * 8];
-    const int j = blockIdx.y, g = blockIdx.z;
-    const uint4* grp = buckets + 8 * (size_t)g * nb;
+// ---- bucket reduction: sum_b b * B_b by rows and columns ------------------------------------------------
+// Bucket index i = b - 1 = hi * 2^lb + lo.  With row sums R_hi = sum_lo B[hi][lo] and column sums
+// C_lo = sum_hi B[hi][lo]:   sum_b b * B_b = 2^lb * sum_hi hi * R_hi + sum_lo (lo + 1) * C_lo.
+// Kernel 1 forms the 2^(c-1-lb) + 2^lb row and column sums (one warp each: strided loads, shuffle tree);
+// kernel 2 bit-slices the two short weighted sums (one warp per weight bit).  About 2 * 2^(c-1) additions
+// instead of the c * 2^(c-2) of bit-slicing all buckets, and two short dependent chains.
+// The last 2c doublings/additions run on the host in microseconds (msm_host_tail).
+// One warp per row / column / weight bit: every lane sums its strided share sequentially, then a five-level
+// shuffle tree.  (A wider tree would shorten the dependent chain but every level of it costs a full
+// addition on all 32 lanes; the sequential share keeps the arithmetic close to the useful 2 * 2^(c-1) additions.)
+// The strided loop and the tree share ONE instance of the ~2300-instruction point addition (a runtime-counted
+// loop whose operand comes from memory or from a shuffle): these warps run alone on their SM sub-partition,
+// so a second copy of the addition per tree level would be paid in instruction-cache misses.
+struct StridedSum {
+    const uint4* base;   // element e lives at base + 8 * (first + e * stride)
+    size_t first, stride;
+    uint32_t count;      // elements in the whole sequence
+    uint32_t filter_bit; // 32: take every element; else take element e iff ((e + filter_bias) >> filter_bit) & 1
+    uint32_t filter_bias;
+};
+
+__device__ __forceinline__ G1Xyzz warp_strided_sum(const StridedSum& q, int lane) {
     G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t b = blockIdx.x * kReduceThreads + threadIdx.x; b < nb; b += kReduceBlocks * kReduceThreads) {
-        if (((b + 1) >> j) & 1u) {
-            G1Xyzz p = G1Xyzz::load(grp + 8 * (size_t)b);
-            acc.add(p);
+    const int nload = (int)((q.count + 31) / 32);
+#pragma unroll 1
+    for (int it = 0; it < nload + 5; it++) {
+        G1Xyzz o = G1Xyzz::identity();
+        if (it < nload) {
+            const uint32_t e = (uint32_t)it * 32u + (uint32_t)lane;
+            const bool take = e < q.count && (q.filter_bit >= 32 || (((e + q.filter_bias) >> q.filter_bit) & 1u));
+            if (take) o = G1Xyzz::load(q.base + 8 * (q.first + (size_t)e * q.stride));
+        } else {
+            o = shfl_xor_point(acc, 16 >> (it - nload), 0xffffffffu);
         }
-    }
-    // warp tree, then one partial per warp through shared memory
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        G1Xyzz o = shfl_xor_point(acc, m, 0xffffffffu);
         acc.add(o);
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) acc.store(sh + 8 * warp);
-    __syncthreads();
-    if (warp == 0) {
-        G1Xyzz v = lane < kReduceThreads / 32 ? G1Xyzz::load(sh + 8 * lane) : G1Xyzz::identity();
-#pragma unroll
-        for (int m = kReduceThreads / 64; m >= 1; m >>= 1) {
-            G1Xyzz o = shfl_xor_point(v, m, 0xffffffffu);
-            v.add(o);
-        }
-        if (lane == 0) v.store(block_out + 8 * ((size_t)(g * c + j) * kReduceBlocks + blockIdx.x));
-    }
+    return acc;  // every lane holds the sum
 }
 
-// one warp per (g, j): fold the kReduceBlocks partials
-__global__ void __launch_bounds__(32) msm_bitreduce_final_kernel(const uint4* __restrict__ block_out, uint4* __restrict__ out) {
-    const int lane = threadIdx.x;
-    const size_t gj = blockIdx.x;
-    G1Xyzz v = lane < kReduceBlocks ? G1Xyzz::load(block_out + 8 * (gj * kReduceBlocks + lane)) : G1Xyzz::identity();
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        G1Xyzz o = shfl_xor_point(v, m, 0xffffffffu);
-        v.add(o);
-    }
-    if (lane == 0) v.store(out + 8 * gj);
+__global__ void __launch_bounds__(kReduceThreads) msm_rowcol_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ rc,
+                                                                    uint32_t nb, int lb) {
+    const uint32_t ncols = 1u << lb, nrows = nb >> lb;
+    const uint32_t g = blockIdx.y;
+    const uint32_t id = blockIdx.x * (kReduceThreads / 32) + (threadIdx.x >> 5);   // warp-uniform
+    const int lane = threadIdx.x & 31;
+    if (id >= nrows + ncols) return;
+    StridedSum q;
+    q.base = buckets + 8 * (size_t)g * nb;
+    q.filter_bit = 32; q.filter_bias = 0;
+    if (id < nrows) { q.first = (size_t)id << lb; q.stride = 1; q.count = ncols; }
+    else { q.first = id - nrows; q.stride = ncols; q.count = nrows; }
+    const G1Xyzz acc = warp_strided_sum(q, lane);
+    if (lane == 0) acc.store(rc + 8 * ((size_t)g * (nrows + ncols) + id));
+}
+
+// out[g][j]: j < rbits -> sum of rows whose index has bit j; else sum of columns whose (index + 1) has bit j - rbits
+__global__ void __launch_bounds__(32) msm_weighted_kernel(const uint4* __restrict__ rc, uint4* __restrict__ out,
+                                                          uint32_t nb, int lb, int c) {
+    const uint32_t ncols = 1u << lb, nrows = nb >> lb;
+    const int rbits = c - 1 - lb;
+    const int j = blockIdx.x, g = blockIdx.y, lane = threadIdx.x;
+    StridedSum q;
+    q.base = rc + 8 * (size_t)g * (nrows + ncols);
+    q.stride = 1;
+    if (j < rbits) { q.first = 0; q.count = nrows; q.filter_bit = (uint32_t)j; q.filter_bias = 0; }
+    else { q.first = nrows; q.count = ncols; q.filter_bit = (uint32_t)(j - rbits); q.filter_bias = 1; }
+    const G1Xyzz acc = warp_strided_sum(q, lane);
+    if (lane == 0) acc.store(out + 8 * ((size_t)g * c + j));
 }
 
 // ---- window tables for a resident basis: table[w*n + i] = 2^(c w) P_i ----------------------------------
@@ -414,16 +441,22 @@ int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b) {
     return ZKW_OK;
 }
 
-// host-side tail: sum_g 2^(c g) sum_j 2^j S[g][j], then affine normalisation
+static inline int rowcol_lb(int c) { return c / 2; }  // column bits of the bucket index split
+
+// host-side tail: sum_g 2^(c g) * (2^lb * sum_j 2^j SR[g][j] + sum_j 2^j SC[g][j]), then affine normalisation
 static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, int c, uint64_t out_xyz[12]) {
+    const int lb = rowcol_lb(c), rbits = c - 1 - lb, cbits = lb + 1;
+    auto at = [&](int g, int j) { G1Xyzz s; memcpy(&s, s_xyzz + 32 * ((size_t)g * c + j), 128); return s; };
     G1Xyzz acc = G1Xyzz::identity();
     for (int g = groups - 1; g >= 0; g--) {
-        for (int j = c - 1; j >= 0; j--) {
-            acc = acc.dbl();
-            G1Xyzz s;
-            memcpy(&s, s_xyzz + 32 * ((size_t)g * c + j), 128);
-            acc.add(s);
-        }
+        for (int d = 0; d < c && g != groups - 1; d++) acc = acc.dbl();
+        G1Xyzz rows = G1Xyzz::identity();
+        for (int j = rbits - 1; j >= 0; j--) { rows = rows.dbl(); rows.add(at(g, j)); }
+        for (int d = 0; d < lb; d++) rows = rows.dbl();
+        G1Xyzz cols = G1Xyzz::identity();
+        for (int j = cbits - 1; j >= 0; j--) { cols = cols.dbl(); cols.add(at(g, rbits + j)); }
+        acc.add(rows);
+        acc.add(cols);
     }
     Fq x = Fq::zero(), y = Fq::one(), z = Fq::zero();
     if (!acc.is_identity()) {
@@ -441,7 +474,7 @@ static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, i
 static int lane_init(zkw_ctx* ctx, int lane) {
     if (!ctx->fork_event) ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     if (lane == 0) { ctx->lane_stream[0] = ctx->stream; }
-    else if (!ctx->lane_stream[lane]) ZKW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[lane], cudaStreamNonBlocking));
+    else if (!ctx->lane_stream[lane]) ZKW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->lane_stream[lane], cudaStreamNonBlocking, stream_priority(0)));
     if (!ctx->lane_done[lane]) ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_done[lane], cudaEventDisableTiming));
     return ZKW_OK;
 }
@@ -482,7 +515,9 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     const size_t o_partials = take(max_slices * 128);
     const size_t o_partials2 = take(max_slices2 * 128);
     const size_t o_buckets = take(tb * 128);
-    const size_t o_blocks = take((size_t)p.groups * c * kReduceBlocks * 128);
+    const int lb = rowcol_lb(c);
+    const uint32_t rc_per_group = (p.nb >> lb) + (1u << lb);
+    const size_t o_blocks = take((size_t)p.groups * rc_per_group * 128);
     const size_t o_out = take((size_t)p.groups * c * 128);
     DeviceBuffer& wsb = lane == 0 ? ctx->msm_ws : ctx->lane_ws[lane];
     if (wsb.bytes < off) {
@@ -518,9 +553,9 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_combine3_kernel", st); msm_combine3_kernel<<<(unsigned)((tb * 32 + 127) / 128), 128, 0, st>>>(partials2, slices2, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_bitreduce_kernel", st); msm_bitreduce_kernel<<<dim3(kReduceBlocks, c, p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, c); }
+    { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<<<dim3((rc_per_group + kReduceThreads / 32 - 1) / (kReduceThreads / 32), p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, lb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_bitreduce_final_kernel", st); msm_bitreduce_final_kernel<<<(unsigned)(p.groups * c), 32, 0, st>>>(blocks, outs); }
+    { ProfScope ps_(ctx, "msm_weighted_kernel", st); msm_weighted_kernel<<<dim3(c, p.groups), 32, 0, st>>>(blocks, outs, p.nb, lb, c); }
     ZKW_LAUNCHED(ctx);
     const size_t out_bytes = (size_t)p.groups * c * 128;
     if (ctx->lane_pinned_bytes[lane] < out_bytes) {
@@ -586,6 +621,13 @@ int msm_lane_submit(zkw_ctx* ctx, int lane, const MsmJob& job) {
     ZKW_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[lane], ctx->fork_event, 0));
     ZKW_TRY(msm_enqueue(ctx, lane, job.which_bases, job.bases_dev, job.scalars_dev, job.n));
     ZKW_CUDA(ctx, cudaEventRecord(ctx->lane_done[lane], ctx->lane_stream[lane]));
+    return ZKW_OK;
+}
+
+int msm_lane_wait(zkw_ctx* ctx, int lane, uint64_t out_xyz[12]) {
+    if (lane < 1 || lane >= zkw_ctx::kMsmLanes || !ctx->lane_done[lane]) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaEventSynchronize(ctx->lane_done[lane]));
+    msm_collect(ctx, lane, out_xyz);
     return ZKW_OK;
 }
 

@@ -84,7 +84,11 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
                 if (s + u == 0) {
                     tv = x[e | (1 << u)];  // stage 0: every twiddle is 1
                 } else {
+#ifdef ZKW_NTT_FAKE_TW   // timing experiment only (wrong results): every twiddle load hits L1
+                    const unsigned idx = ((jm + (el << s)) << sh) & 63u;
+#else
                     const unsigned idx = (jm + (el << s)) << sh;
+#endif
                     Fr w = Fr::load_nc(a.tw + 2 * (size_t)idx);
                     tv = x[e | (1 << u)] * w;
                 }

@@ -200,33 +200,54 @@ static int commit_batch(zkw_ctx* ctx, Transcript& tr, const std::vector<std::pai
 }
 
 // Pipelined commitments: each polynomial's MSM is submitted to a side lane the moment the polynomial is
-// queued on the main stream, which keeps producing the next one; flush() collects in submission order.
+// queued on the main stream, which keeps producing the next one.  submit() returns a ticket; write(ticket)
+// waits for that MSM only and appends its commitment to the transcript, so commitments whose polynomials do
+// not depend on a challenge (permuted lookup columns, the random polynomial) can be computed rounds before
+// the transcript absorbs them.  When every lane is busy the oldest ticket is retired into `done` first.
 struct LanePipe {
     zkw_ctx* ctx;
     Transcript& tr;
     size_t n;
-    std::vector<int> lanes;
-    LanePipe(zkw_ctx* c, Transcript& t, size_t n_) : ctx(c), tr(t), n(n_) {}
-    int submit(int which, const uint64_t* poly) {
-        if ((int)lanes.size() == zkw_ctx::kMsmLanes - 1) ZKW_TRY(flush());
-        const int lane = 1 + (int)lanes.size();
-        ZKW_TRY(msm_lane_submit(ctx, lane, MsmJob{which, nullptr, poly, n}));
-        lanes.push_back(lane);
+    struct Slot { int lane; bool ready, written; std::array<uint64_t, 8> xy; };
+    std::vector<Slot> slots;     // by ticket
+    std::vector<int> lane_owner; // lane -> ticket in flight, or -1
+    LanePipe(zkw_ctx* c, Transcript& t, size_t n_) : ctx(c), tr(t), n(n_), lane_owner(zkw_ctx::kMsmLanes, -1) {}
+    int retire(int ticket) {
+        Slot& s = slots[ticket];
+        if (s.ready) return ZKW_OK;
+        uint64_t xyz[12];
+        ZKW_TRY(msm_lane_wait(ctx, s.lane, xyz));
+        memcpy(s.xy.data(), xyz, 64);
+        bool ident = true;
+        for (int i = 8; i < 12; i++) ident = ident && xyz[i] == 0;
+        if (ident) s.xy.fill(0);
+        s.ready = true;
+        lane_owner[s.lane] = -1;
         return ZKW_OK;
     }
-    int flush() {
-        if (lanes.empty()) return ZKW_OK;
-        std::vector<std::array<uint64_t, 12>> outs(lanes.size());
-        ZKW_TRY(msm_lanes_collect(ctx, lanes.data(), (int)lanes.size(), reinterpret_cast<uint64_t(*)[12]>(outs.data())));
-        for (auto& o : outs) {
-            uint64_t xy[8];
-            memcpy(xy, o.data(), 64);
-            bool ident = true;
-            for (int i = 8; i < 12; i++) ident = ident && o[i] == 0;
-            if (ident) memset(xy, 0, 64);
-            tr.write_point(xy);
+    int submit(int which, const uint64_t* poly, int* ticket = nullptr) {
+        int lane = -1;
+        for (int l = 1; l < zkw_ctx::kMsmLanes; l++) if (lane_owner[l] < 0) { lane = l; break; }
+        if (lane < 0) {
+            int oldest = -1;
+            for (int l = 1; l < zkw_ctx::kMsmLanes; l++) if (oldest < 0 || lane_owner[l] < oldest) { oldest = lane_owner[l]; lane = l; }
+            ZKW_TRY(retire(oldest));
         }
-        lanes.clear();
+        ZKW_TRY(msm_lane_submit(ctx, lane, MsmJob{which, nullptr, poly, n}));
+        slots.push_back(Slot{lane, false, false, {}});
+        lane_owner[lane] = (int)slots.size() - 1;
+        if (ticket) *ticket = (int)slots.size() - 1;
+        return ZKW_OK;
+    }
+    int write(int ticket) {
+        ZKW_TRY(retire(ticket));
+        if (!slots[ticket].written) tr.write_point(slots[ticket].xy.data());
+        slots[ticket].written = true;
+        return ZKW_OK;
+    }
+    // every ticket not yet written, in submission order
+    int flush() {
+        for (int t = 0; t < (int)slots.size(); t++) if (!slots[t].written) ZKW_TRY(write(t));
         return ZKW_OK;
     }
 };
@@ -506,7 +527,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     // coset (zeta-coset NTT) are computed there, overlapping the commitments running on the main stream
     // and the MSM lanes.  The main stream joins before the quotient kernel.
     if (!ctx->aux_stream) {
-        ZKW_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        ZKW_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, stream_priority(1)));
         ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
         ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
     }
@@ -551,13 +572,13 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         ZKW_TRY(rand_fill(ctx, adv[c] + 4 * u, n - u, seed, 1 + c, 0));
         ZKW_TRY(spawn_transform(adv[c], &adv_cf[c], &e_adv[c]));
     }
-    {
-        std::vector<std::pair<int, const uint64_t*>> polys;
-        for (unsigned c = 0; c < NA; c++) polys.push_back({ZKW_BASES_G_LAGRANGE, adv[c]});
-        ZKW_TRY(commit_batch(ctx, tr, polys, n));
-    }
-    const Fr theta = tr.squeeze();
-    (void)theta;  // single-expression lookups: theta-compression is the identity
+    // Commitments of this and the next two rounds that do not depend on a challenge are all started now, each on
+    // its own MSM lane: the advice columns, the permuted lookup columns (single-expression lookups: the theta
+    // compression is the identity, so A' and S' are functions of the witness alone) and the random polynomial of
+    // the vanishing argument.  The transcript still absorbs them in upstream's order (pipe.write below).
+    LanePipe pipe(ctx, tr, n);
+    std::vector<int> t_adv(NA), t_lk;
+    for (unsigned c = 0; c < NA; c++) ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, adv[c], &t_adv[c]));
 
     // ---- 2. lookups: permuted input / table ----
     uint64_t *num, *den, *pn, *sd, *blocks, *total_dev;
@@ -597,16 +618,30 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_TRY(spawn_transform(lk_a[l], &lk_a_cf[l], &e_la[l]));
             ZKW_TRY(spawn_transform(lk_s[l], &lk_s_cf[l], &e_ls[l]));
         }
-        std::vector<std::pair<int, const uint64_t*>> polys;
-        for (unsigned l = 0; l < nlk; l++) { polys.push_back({ZKW_BASES_G_LAGRANGE, lk_a[l]}); polys.push_back({ZKW_BASES_G_LAGRANGE, lk_s[l]}); }
-        ZKW_TRY(commit_batch(ctx, tr, polys, n));
+        for (unsigned l = 0; l < nlk; l++) {
+            int ta, ts;
+            ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, lk_a[l], &ta));
+            ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, lk_s[l], &ts));
+            t_lk.push_back(ta); t_lk.push_back(ts);
+        }
     }
+    // vanishing argument: the random polynomial (committed after the grand products, computed now)
+    uint64_t* random_poly;
+    int t_random;
+    ZKW_TRY(sc.get(vb, (void**)&random_poly));
+    ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
+    ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
+
+    for (int t : t_adv) ZKW_TRY(pipe.write(t));
+    const Fr theta = tr.squeeze();
+    (void)theta;
+    for (int t : t_lk) ZKW_TRY(pipe.write(t));
     const Fr beta = tr.squeeze();
     const Fr gamma = tr.squeeze();
 
     // ---- 3. permutation grand products ----
     std::vector<uint64_t*> perm_z(nsets);
-    LanePipe zpipe(ctx, tr, n);
+    std::vector<int> t_z;
     {
         const Fr delta = fr_of(kDeltaM);
         Fr dpow = Fr::one();
@@ -627,7 +662,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
             ZKW_LAUNCHED(ctx);
             const uint64_t* z0 = s ? perm_z[s - 1] + 4 * u : nullptr;
             ZKW_TRY(grand_product(ctx, num, den, pn, sd, blocks, total_dev, z0, perm_z[s], u, n, seed, 2000 + s));
-            ZKW_TRY(zpipe.submit(ZKW_BASES_G_LAGRANGE, perm_z[s]));
+            { int t; ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, perm_z[s], &t)); t_z.push_back(t); }
             ZKW_TRY(spawn_transform(perm_z[s], &perm_z_cf[s], &e_pz[s]));
         }
     }
@@ -636,15 +671,12 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         { ProfScope ps_(ctx, "lookup_numden_kernel"); lookup_numden_kernel<<<grid_for(n, 128), 128, 0, st>>>((const uint4*)lk_inp[l], (const uint4*)pk->fixed_values[pk->table_col()], (const uint4*)lk_a[l], (const uint4*)lk_s[l], beta, gamma, (uint4*)num, (uint4*)den, n); }
         ZKW_LAUNCHED(ctx);
         ZKW_TRY(grand_product(ctx, num, den, pn, sd, blocks, total_dev, nullptr, lk_z[l], u, n, seed, 3000 + l));
-        ZKW_TRY(zpipe.submit(ZKW_BASES_G_LAGRANGE, lk_z[l]));
+        { int t; ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, lk_z[l], &t)); t_z.push_back(t); }
         ZKW_TRY(spawn_transform(lk_z[l], &lk_z_cf[l], &e_lz[l]));
     }
-    // ---- 5. vanishing argument: random polynomial; commitments of this round in one batch ----
-    uint64_t* random_poly;
-    ZKW_TRY(sc.get(vb, (void**)&random_poly));
-    ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
-    ZKW_TRY(zpipe.submit(ZKW_BASES_G, random_poly));
-    ZKW_TRY(zpipe.flush());
+    // ---- 5. transcript: grand products, then the random polynomial's commitment ----
+    for (int t : t_z) ZKW_TRY(pipe.write(t));
+    ZKW_TRY(pipe.write(t_random));
     const Fr y = tr.squeeze();
 
     // ---- 6. quotient ----
