@@ -232,6 +232,15 @@ enum { ZKW_ADVICE_ON_DEVICE = 1, ZKW_ADVICE_CANONICAL = 2, ZKW_MULTIOPEN_SHPLONK
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
                         uint64_t seed, int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* Host-side witness synthesis for the shape-identical synthetic ECDSA circuit (stands in for
+ * ECDSACircuit::synthesize, halo2-circuits/src/ecc/ecdsa_p256.rs:117-206, whose halo2-ecc chips are un-vendored):
+ * fills cols_out[c] (c < num_advice: 4 * floor((2^k - blinding_factors - 1) / 4) cells; lookup-advice columns:
+ * 2^k - blinding_factors - 1 cells) with canonical values < 2^64 keyed by the assertion bytes, and rows_out[c]
+ * (may be NULL) with the cell counts.  Pure host code: no device, no context.  Feed the columns to
+ * zkw_create_proof_ex with ZKW_ADVICE_U64. */
+int zkw_synth_witness(const zkw_circuit_shape* shape, uint32_t lookup_bits, const uint8_t* assertion, size_t assertion_len,
+                      uint64_t* const* cols_out, size_t* rows_out);
+
 /* Fr vectors between canonical little-endian integers (< 2r accepted) and halo2curves' Montgomery form;
  * host pointers, n elements of 4 u64. */
 int zkw_fr_to_mont(zkw_ctx* ctx, const uint64_t* canonical, uint64_t* out, size_t n);
@@ -240,6 +249,9 @@ int zkw_fr_from_mont(zkw_ctx* ctx, const uint64_t* mont, uint64_t* out, size_t n
 /* ---- device memory helpers for FFI callers that keep polynomials resident -------------------- */
 int zkw_dev_alloc(zkw_ctx* ctx, size_t bytes, void** out_dev);
 int zkw_dev_free(zkw_ctx* ctx, void* dev);
+/* page-locked host memory: witness columns synthesised into it reach the device with one asynchronous copy */
+int zkw_host_alloc(zkw_ctx* ctx, size_t bytes, void** out_host);
+int zkw_host_free(zkw_ctx* ctx, void* host);
 int zkw_memcpy_h2d(zkw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 int zkw_memcpy_d2h(zkw_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 

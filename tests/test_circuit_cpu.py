@@ -58,3 +58,18 @@ def test_validate_assertion_mirrors_reference_unwraps(zkw):
                 (b"\xff" * 32, gy, ok, ok, ok)]:
         with pytest.raises(ValueError):
             zkw.validate_assertion(*bad)
+
+
+@pytest.mark.parametrize("degree", [19, 17, 12, 7])
+def test_native_synthesis_matches_numpy_statement(zkw, degree):
+    """zkw_synth_witness (host C++ in the library, the routine inside the timed end-to-end path) and
+    SyntheticEcdsaCircuit.synthesize (numpy) fill the same cells."""
+    params = zkw.CircuitParams.for_degree(degree) if degree != 7 else zkw.CircuitParams("Simple", 7, 4, 1, 1, 6, 88, 3)
+    circ = zkw.SyntheticEcdsaCircuit(params)
+    shape = zkw.CircuitShape.from_config(params.degree, params.num_advice, params.num_lookup_advice, params.num_fixed)
+    for assertion in (b"", b"assertion-1", bytes(range(160))):
+        want = circ.synthesize(assertion)
+        got = zkw.native.synth_witness(shape, params.lookup_bits, assertion)
+        assert len(want) == len(got)
+        for w, g in zip(want, got):
+            assert w.shape == g.shape and (w == g).all()

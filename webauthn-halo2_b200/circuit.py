@@ -149,37 +149,51 @@ class SyntheticEcdsaCircuit:
 
     # -- witness side --------------------------------------------------------------------------------
     def synthesize(self, assertion: bytes) -> list[np.ndarray]:
-        """Advice columns' usable rows as canonical (rows,) uint64 arrays, keyed by the assertion bytes."""
-        G, u = self.G, self.u
-        seed = int.from_bytes(hashlib.sha256(b"zkw-b200-synth" + assertion).digest()[:8], "little")
-        rng = np.random.default_rng(seed)
-        const0 = (np.arange(8, dtype=np.uint64) + 1)
+        """Advice columns' usable rows as canonical (rows,) uint64 arrays, keyed by the assertion bytes.
+        numpy statement of the generator that the library's host routine zkw_synth_witness (csrc/witness.cu)
+        runs inside the timed end-to-end path; tests/test_circuit_cpu.py checks the two agree cell for cell."""
+        G, u, T = self.G, self.u, self.T
+        seed = int.from_bytes(hashlib.blake2b(b"zkw-b200-synth" + assertion).digest()[:8], "little")
+        pow2 = T & (T - 1) == 0
+        U = np.uint64
+
+        def mix64(z):   # splitmix64 finaliser over a counter (uint64 arithmetic wraps)
+            z = (z ^ (z >> U(30))) * U(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> U(27))) * U(0x94D049BB133111EB)
+            return z ^ (z >> U(31))
+
+        def stream(col_index):
+            return U((seed ^ (0x9E3779B97F4A7C15 * (col_index + 1))) & 0xFFFFFFFFFFFFFFFF)
+
         cols = []
-        for c in range(self.A):
-            a = rng.integers(0, 1 << 62, size=G, dtype=np.uint64)
-            bits = rng.integers(0, 2, size=G, dtype=np.uint64)
-            a = np.where(rng.integers(0, 2, size=G) == 1, bits, a)          # mix of bits and wide limbs
-            b = rng.integers(0, self.T, size=G, dtype=np.uint64)
-            cc = rng.integers(0, 1 << 40, size=G, dtype=np.uint64)
-            if c == 0:
-                nconst = min(8, (G + 1) // 2, u)
-                a[0:2 * nconst:2] = const0[:nconst]
-            d = np.empty(G, dtype=np.uint64)
-            bc = b * cc
-            # even gates are free, odd gates take a = d of the previous (even) gate
-            d[0::2] = a[0::2] + bc[0::2]
-            if G > 1:
-                a[1::2] = d[0::2][: a[1::2].shape[0]]
-                d[1::2] = a[1::2] + bc[1::2]
-            col = np.zeros(4 * G, dtype=np.uint64)
-            col[0::4], col[1::4], col[2::4], col[3::4] = a, b, cc, d
-            cols.append(col)
-        for l in range(self.L):
-            col = rng.integers(0, self.T, size=u, dtype=np.uint64)
-            if l == 0:
-                jj = np.arange(0, min(G, u), 3)
-                col[jj] = cols[0][4 * jj + 1]
-            cols.append(col)
+        with np.errstate(over="ignore"):
+            g3 = U(3) * np.arange(G, dtype=np.uint64)
+            for c in range(self.A):
+                s = stream(c)
+                r1, r2, r3 = mix64(s + g3), mix64(s + g3 + U(1)), mix64(s + g3 + U(2))
+                # a: a mix of bits and wide (62-bit) limbs; b < T is the range-checked cell; c < 2^40
+                a = np.where(r2 >> U(63) != 0, (r2 >> U(62)) & U(1), r1 >> U(2))
+                b = (r3 & U(T - 1)) if pow2 else (r3 % U(T))
+                cc = (r2 >> U(8)) & U((1 << 40) - 1)
+                if c == 0:
+                    nconst = min(8, (G + 1) // 2)
+                    a[0:2 * nconst:2] = np.arange(1, nconst + 1, dtype=np.uint64)
+                bc = b * cc
+                # even gates are free, odd gates take a = d of the previous (even) gate
+                d_even = a[0::2] + bc[0::2]
+                if G > 1:
+                    a[1::2] = d_even[: a[1::2].shape[0]]
+                col = np.empty(4 * G, dtype=np.uint64)
+                quad = col.reshape(G, 4)
+                quad[:, 0], quad[:, 1], quad[:, 2], quad[:, 3] = a, b, cc, a + bc
+                cols.append(col)
+            for l in range(self.L):
+                r = mix64(stream(self.A + l) + np.arange(u, dtype=np.uint64))
+                col = (r & U(T - 1)) if pow2 else (r % U(T))
+                if l == 0:
+                    jj = np.arange(0, min(G, u), 3)
+                    col[jj] = cols[0][4 * jj + 1]
+                cols.append(col)
         return cols
 
 

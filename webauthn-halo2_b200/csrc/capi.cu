@@ -319,6 +319,18 @@ int zkw_dev_free(zkw_ctx* ctx, void* dev) {
     ZKW_CUDA(ctx, cudaFree(dev));
     return ZKW_OK;
 }
+int zkw_host_alloc(zkw_ctx* ctx, size_t bytes, void** out_host) {
+    CTX_ENTER(ctx);
+    if (!out_host) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaHostAlloc(out_host, bytes ? bytes : 1, cudaHostAllocDefault));
+    return ZKW_OK;
+}
+int zkw_host_free(zkw_ctx* ctx, void* host) {
+    CTX_ENTER(ctx);
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ZKW_CUDA(ctx, cudaFreeHost(host));
+    return ZKW_OK;
+}
 int zkw_memcpy_h2d(zkw_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     CTX_ENTER(ctx);
     ZKW_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));

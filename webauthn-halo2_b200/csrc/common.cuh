@@ -47,6 +47,7 @@ struct zkw_ctx {
     // MSM tuning: window bits (0 = automatic) and whether fixed bases get window tables
     int msm_window_bits = 0;
     int msm_precompute = 1;
+    bool msm_attr_set = false;           // accumulate kernel's dynamic shared memory opt-in done
 
     // twiddle tables: omega^i for i < 2^(log_n-1), keyed by (omega, log_n)
     std::map<zkw::TwiddleKey, zkw::DeviceBuffer> twiddles;

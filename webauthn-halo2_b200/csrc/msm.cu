@@ -13,28 +13,42 @@
 //              per window (G = W) and the windows are combined on the host.
 //   sort       counting sort of the (window, point) entries by bucket: histogram (atomics in L2),
 //              single-CTA scan, scatter.
-//   accumulate the sorted entry list is cut into bucket-aligned slices of <= kSlice entries; one
-//              thread sums one slice with mixed XYZZ additions (8M + 2S each), prefetching the next
-//              affine point (two 128-bit loads per coordinate) while it adds the current one.  Work
-//              per thread is bounded whatever the scalar distribution (witness columns are far from
-//              uniform: zeros, bits, small limbs).
-//   combine    two levels: one thread folds up to kSlice2 slice sums; then one warp per bucket folds what
-//              is left (one copy for almost every bucket, a strided loop + shuffle tree for heavy ones).
+//   accumulate the sorted entry list is cut into EQUAL runs of L = ceil(E / T) entries, T = one resident
+//              wave of threads (CTAs per SM x SMs x 128), so the grid is exactly one wave and every thread
+//              does the same number of mixed XYZZ additions (8M + 2S each) whatever the scalar distribution
+//              (witness columns are far from uniform: zeros, bits, small limbs) - no partial last wave.
+//              A run crosses bucket boundaries: thread t emits its sum for bucket b to partial slot t + b
+//              (strictly increasing along the entry list, so a bucket's partials are contiguous and their
+//              range follows from the bucket's offsets alone).  The next affine point is prefetched (two
+//              128-bit loads per coordinate) while the current one is added.
+//   combine    one thread per bucket folds its (typically 3-4) partials; buckets cut into more than
+//              kLight runs (skewed scalars) get one warp each: strided loop + shuffle tree.
 //   reduce     sum_b b * B_b by rows and columns of the bucket index (b - 1 = hi * 2^lb + lo): tree sums of
 //              every row and column, then two short bit-sliced weighted sums; the final ~2c-step Horner
 //              runs on the host in microseconds instead of as a latency-bound chain on the device.
 //
 // The kernels are integer-ALU bound: 96 algorithmic bytes per point against ~10 field products per
 // window per point.  DESIGN.md carries the roofline arithmetic.
+#include <algorithm>
 #include "common.cuh"
 
 namespace zkw {
 
-#ifndef ZKW_MSM_SLICE
-#define ZKW_MSM_SLICE 32
+// Resident accumulate CTAs per SM: 120 registers x 128 threads allow four.  ZKW_MSM_SMEM_RESERVE > 0 makes the
+// kernel ask for that much dynamic shared memory it never touches, which caps the residency of accumulate CTAs
+// from all MSM lanes together and keeps a CTA slot per SM free for the short kernels of other streams.  Measured
+// (tools/msm_ab.py, k = 19 proof): 4 CTAs / no reserve 28.2 ms, 3 CTAs + 64 KB 28.7 ms, 2 CTAs + 96 KB 29.6 ms -
+// four warps per scheduler hide the multiplier latency better than three, and that outweighs the free slot.
+#ifndef ZKW_MSM_CTAS_PER_SM
+#define ZKW_MSM_CTAS_PER_SM 4
 #endif
-constexpr int kSlice = ZKW_MSM_SLICE;         // entries per accumulate thread
-constexpr int kSlice2 = 16;        // slice sums per second-level combine thread
+#ifndef ZKW_MSM_SMEM_RESERVE
+#define ZKW_MSM_SMEM_RESERVE 0
+#endif
+constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
+constexpr int kAccThreads = 128;
+constexpr int kMinRun = 16;        // shortest run worth a thread (small MSMs use fewer threads instead)
+constexpr int kLight = 8;          // partials per bucket folded by one thread; more -> one warp
 constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
 struct MsmPlan {
@@ -45,9 +59,10 @@ struct MsmPlan {
     size_t n;
     size_t max_entries() const { return (size_t)windows * n; }
     size_t total_buckets() const { return (size_t)groups * nb; }
-    size_t max_slices() const { return max_entries() / kSlice + total_buckets(); }
-    size_t max_slices2() const { return max_slices() / kSlice2 + total_buckets(); }
 };
+
+// device-side run plan, written by the scan kernel once the number of entries is known
+struct RunPlan { uint32_t entries, run, threads, heavy; };  // heavy: buckets queued for msm_combine_heavy_kernel
 
 // ---- recode + histogram -----------------------------------------------------------------------
 __global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ digits,
@@ -82,7 +97,7 @@ __global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* _
     }
 }
 
-// ---- single-CTA exclusive scans: bucket offsets, slice starts, second-level slice starts -------
+// ---- single-CTA exclusive scan of the bucket counts -> bucket offsets; also fixes the run length ------
 // Tiles of 4096 counts (one uint4 per thread, coalesced); per tile a warp-shuffle scan of the thread
 // totals, a scan of the 32 warp totals, and a running carry.
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
@@ -95,12 +110,11 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 }
 
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                                        uint32_t* __restrict__ slice_start, uint32_t* __restrict__ slice2_start,
-                                                        size_t total) {
-    __shared__ uint32_t wsum[3][32];
-    __shared__ uint32_t carry[3];
+                                                        RunPlan* __restrict__ plan, size_t total, uint32_t max_threads) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t < 3) carry[t] = 0;
+    if (t == 0) carry = 0;
     __syncthreads();
     for (size_t base = 0; base < total; base += 4096) {
         const size_t idx = base + 4 * (size_t)t;
@@ -111,41 +125,31 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
         } else {
             for (int j = 0; j < 4; j++) if (idx + j < total) cnt[j] = counts[idx + j];
         }
-        uint32_t q[3][4], tot[3] = {0, 0, 0};
+        const uint32_t tot = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        const uint32_t inc = warp_inclusive_scan(tot, lane);
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        if (warp == 0) wsum[lane] = warp_inclusive_scan(wsum[lane], lane);
+        __syncthreads();
+        uint32_t run = carry + (warp ? wsum[warp - 1] : 0u) + inc - tot;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const uint32_t s1 = (cnt[j] + kSlice - 1) / kSlice;
-            q[0][j] = cnt[j]; q[1][j] = s1; q[2][j] = (s1 + kSlice2 - 1) / kSlice2;
-            tot[0] += q[0][j]; tot[1] += q[1][j]; tot[2] += q[2][j];
-        }
-        uint32_t inc[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            inc[k] = warp_inclusive_scan(tot[k], lane);
-            if (lane == 31) wsum[k][warp] = inc[k];
+            if (idx + j < total) { offsets[idx + j] = run; run += cnt[j]; }
         }
         __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) wsum[k][lane] = warp_inclusive_scan(wsum[k][lane], lane);
-        }
-        __syncthreads();
-        uint32_t run[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) run[k] = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - tot[k];
-        uint32_t* outs[3] = {offsets, slice_start, slice2_start};
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (idx + j < total) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) { outs[k][idx + j] = run[k]; run[k] += q[k][j]; }
-            }
-        }
-        __syncthreads();
-        if (t < 3) carry[t] += wsum[t][31];
+        if (t == 0) carry += wsum[31];
         __syncthreads();
     }
-    if (t == 0) { offsets[total] = carry[0]; slice_start[total] = carry[1]; slice2_start[total] = carry[2]; }
+    if (t == 0) {
+        const uint32_t e = carry;
+        offsets[total] = e;
+        uint32_t run = (e + max_threads - 1) / max_threads;
+        if (run < (uint32_t)kMinRun) run = kMinRun;
+        plan->entries = e;
+        plan->run = run;
+        plan->threads = (e + run - 1) / run;
+        plan->heavy = 0;
+    }
 }
 
 // ---- scatter entries into bucket order ----------------------------------------------------------
@@ -164,43 +168,42 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ digits, const ui
     sorted[pos] = (d & 0x80000000u) | pidx;
 }
 
-// ---- accumulate: one thread per slice -------------------------------------------------------------
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const uint4* __restrict__ points, const uint32_t* __restrict__ sorted,
-                                                             const uint32_t* __restrict__ offsets,
-                                                             const uint32_t* __restrict__ slice_start, uint4* __restrict__ partials,
-                                                             uint32_t total_buckets) {
-    const uint32_t sl = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nslices = slice_start[total_buckets];
-    if (sl >= nslices) return;
-    // bucket of this slice: last b with slice_start[b] <= sl (empty buckets share a start with the next)
-    uint32_t lo = 0, hi = total_buckets;  // invariant: slice_start[lo] <= sl < slice_start[hi]
+// ---- accumulate: one thread per run of plan->run consecutive sorted entries ----------------------------
+__global__ void __launch_bounds__(kAccThreads, ZKW_MSM_CTAS_PER_SM)
+msm_accumulate_kernel(const uint4* __restrict__ points, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets,
+                      const RunPlan* __restrict__ plan, uint4* __restrict__ partials, uint32_t total_buckets) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t run = plan->run, entries = plan->entries;
+    if (t >= plan->threads) return;
+    const uint32_t begin = t * run;
+    const uint32_t end = begin + run < entries ? begin + run : entries;
+    // bucket of the first entry: last b with offsets[b] <= begin (empty buckets share an offset with the next)
+    uint32_t lo = 0, hi = total_buckets;  // invariant: offsets[lo] <= begin < offsets[hi]
     while (hi - lo > 1) {
         const uint32_t mid = (lo + hi) >> 1;
-        if (slice_start[mid] <= sl) lo = mid; else hi = mid;
+        if (offsets[mid] <= begin) lo = mid; else hi = mid;
     }
-    const uint32_t b = lo;
-    const uint32_t begin = offsets[b] + (sl - slice_start[b]) * kSlice;
-    const uint32_t bend = offsets[b + 1];
-    const uint32_t end = begin + kSlice < bend ? begin + kSlice : bend;
+    uint32_t b = lo;
+    uint32_t bend = offsets[b + 1];
     uint32_t e = sorted[begin];
     G1Affine cur = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
-    if (e >> 31) cur.y = cur.y.neg();
-    G1Xyzz acc = G1Xyzz::from_affine(cur);
-    if (begin + 1 < end) {
-        e = sorted[begin + 1];
-        cur = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
-        for (uint32_t k = begin + 1; k < end; k++) {
-            const bool neg = e >> 31;
-            G1Affine nxt = cur;
-            if (k + 1 < end) {
-                e = sorted[k + 1];
-                nxt = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
-            }
-            acc.add_mixed(cur, neg);
-            cur = nxt;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t k = begin; k < end; k++) {
+        const bool neg = e >> 31;
+        G1Affine nxt = cur;
+        if (k + 1 < end) {
+            e = sorted[k + 1];
+            nxt = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
         }
+        if (k == bend) {   // entry k opens the next non-empty bucket: emit the finished one
+            acc.store(partials + 8 * ((size_t)t + b));
+            acc = G1Xyzz::identity();
+            do { b++; bend = offsets[b + 1]; } while (bend <= k);
+        }
+        acc.add_mixed(cur, neg);
+        cur = nxt;
     }
-    acc.store(partials + 8 * (size_t)sl);
+    acc.store(partials + 8 * ((size_t)t + b));
 }
 
 __device__ __forceinline__ G1Xyzz shfl_xor_point(const G1Xyzz& p, int lane_mask, unsigned member_mask) {
@@ -215,65 +218,76 @@ __device__ __forceinline__ G1Xyzz shfl_xor_point(const G1Xyzz& p, int lane_mask,
     return r;
 }
 
-// ---- combine, level 2: one thread folds up to kSlice2 slice sums of one bucket ----------------------
-__device__ __forceinline__ uint32_t last_start_le(const uint32_t* __restrict__ start, uint32_t n, uint32_t x) {
-    uint32_t lo = 0, hi = n;  // invariant: start[lo] <= x < start[hi]
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (start[mid] <= x) lo = mid; else hi = mid;
-    }
-    return lo;
+// ---- combine: bucket b's partials live in slots t + b, t = first run .. last run touching the bucket ----
+__device__ __forceinline__ bool bucket_partials(const uint32_t* __restrict__ offsets, uint32_t run, uint32_t b, size_t* first, uint32_t* count) {
+    const uint32_t o0 = offsets[b], o1 = offsets[b + 1];
+    if (o1 == o0) { *count = 0; *first = 0; return false; }
+    const uint32_t t0 = o0 / run, t1 = (o1 - 1) / run;
+    *first = (size_t)t0 + b;
+    *count = t1 - t0 + 1;
+    return true;
 }
 
-__global__ void __launch_bounds__(128) msm_combine2_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ slice_start,
-                                                           const uint32_t* __restrict__ slice2_start, uint4* __restrict__ partials2,
-                                                           uint32_t total_buckets) {
-    const uint32_t sl2 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sl2 >= slice2_start[total_buckets]) return;
-    const uint32_t b = last_start_le(slice2_start, total_buckets, sl2);
-    const uint32_t begin = slice_start[b] + (sl2 - slice2_start[b]) * kSlice2;
-    const uint32_t bend = slice_start[b + 1];
-    const uint32_t end = begin + kSlice2 < bend ? begin + kSlice2 : bend;
-    G1Xyzz acc = G1Xyzz::load(partials + 8 * (size_t)begin);
-    for (uint32_t s = begin + 1; s < end; s++) {
-        G1Xyzz p = G1Xyzz::load(partials + 8 * (size_t)s);
+// one thread per bucket: folds up to kLight partials (the common case); heavier buckets are queued for the CTA kernel
+__global__ void __launch_bounds__(128) msm_combine_light_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
+                                                                RunPlan* __restrict__ plan, uint32_t* __restrict__ heavy_list,
+                                                                uint4* __restrict__ buckets, uint32_t total_buckets) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total_buckets) return;
+    size_t first;
+    uint32_t count;
+    bucket_partials(offsets, plan->run, b, &first, &count);
+    if (count > (uint32_t)kLight) { heavy_list[atomicAdd(&plan->heavy, 1u)] = b; return; }
+    G1Xyzz acc = G1Xyzz::identity();   // all-zero = identity (ZZ = 0): what an empty bucket stores
+    if (count) acc = G1Xyzz::load(partials + 8 * first);
+    for (uint32_t i = 1; i < count; i++) {
+        G1Xyzz p = G1Xyzz::load(partials + 8 * (first + i));
         acc.add(p);
     }
-    acc.store(partials2 + 8 * (size_t)sl2);
+    acc.store(buckets + 8 * (size_t)b);
 }
 
-// ---- combine, level 3: one warp per bucket folds whatever level-2 sums the bucket has -----------------
-// Almost every bucket has exactly one (copy) — only heavy buckets (skewed scalars: zeros, bits, tiny
-// digits of sorted lookup columns) reach the strided loop and the shuffle tree (one shared instance of the
-// point addition: runtime-counted loop, operand from memory or from a shuffle).
-__global__ void __launch_bounds__(128) msm_combine3_kernel(const uint4* __restrict__ partials2, const uint32_t* __restrict__ slice2_start,
-                                                           uint4* __restrict__ buckets, uint32_t total_buckets) {
-    const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (b >= total_buckets) return;  // whole warps leave together
-    const uint32_t s0 = slice2_start[b], s1 = slice2_start[b + 1];
-    if (s1 - s0 <= 1) {
-        if (lane < 8) {
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (s1 > s0) v = partials2[8 * (size_t)s0 + lane];
-            buckets[8 * (size_t)b + lane] = v;   // 128 bytes = 8 x uint4; all-zero is the identity (ZZ = 0)
-        }
-        return;
-    }
-    G1Xyzz acc = G1Xyzz::identity();
-    const int nload = (int)((s1 - s0 + 31) / 32);
+// one CTA per queued bucket (grid-stride over the list), i.e. buckets cut into more than kLight runs (skewed scalars: zeros, bits,
+// tiny digits of sorted lookup columns, long constant stretches of a grand product): strided loop, shuffle
+// tree, then the eight warp sums through shared memory - all sharing one instance of the point addition
+// (runtime-counted loop whose operand comes from memory, from a shuffle, or from shared memory)
+constexpr int kHeavyThreads = 256;
+__global__ void __launch_bounds__(kHeavyThreads) msm_combine_heavy_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
+                                                                          const RunPlan* __restrict__ plan, const uint32_t* __restrict__ heavy_list,
+                                                                          uint4* __restrict__ buckets) {
+    __shared__ uint4 sh[(kHeavyThreads / 32) * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t nheavy = plan->heavy;
 #pragma unroll 1
-    for (int it = 0; it < nload + 5; it++) {
+    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    const uint32_t b = heavy_list[h];
+    size_t first;
+    uint32_t count;
+    bucket_partials(offsets, plan->run, b, &first, &count);
+    G1Xyzz acc = G1Xyzz::identity();
+    const int nload = (int)((count + kHeavyThreads - 1) / kHeavyThreads);
+    const int total_it = nload + 5 + 3;
+#pragma unroll 1
+    for (int it = 0; it < total_it; it++) {
+        if (it == nload + 5) {   // every lane of a warp holds the warp's sum: hand the 8 sums to warp 0
+            if (lane == 0) acc.store(sh + 8 * warp);
+            __syncthreads();
+            acc = (warp == 0 && lane < kHeavyThreads / 32) ? G1Xyzz::load(sh + 8 * lane) : G1Xyzz::identity();
+        }
         G1Xyzz o = G1Xyzz::identity();
         if (it < nload) {
-            const uint32_t s = s0 + (uint32_t)it * 32u + (uint32_t)lane;
-            if (s < s1) o = G1Xyzz::load(partials2 + 8 * (size_t)s);
-        } else {
+            const uint32_t i = (uint32_t)it * kHeavyThreads + threadIdx.x;
+            if (i < count) o = G1Xyzz::load(partials + 8 * (first + i));
+        } else if (it < nload + 5) {
             o = shfl_xor_point(acc, 16 >> (it - nload), 0xffffffffu);
+        } else {
+            o = shfl_xor_point(acc, 4 >> (it - nload - 5), 0xffffffffu);
         }
         acc.add(o);
     }
-    if (lane == 0) acc.store(buckets + 8 * (size_t)b);
+    if (threadIdx.x == 0) acc.store(buckets + 8 * (size_t)b);
+    __syncthreads();   // sh is reused by the next queued bucket
+    }
 }
 
 // ---- bucket reduction: sum_b b * B_b by rows and columns ------------------------------------------------
@@ -501,8 +515,9 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     make_plan(p, n, c, table);
     if (p.max_entries() >= (1ull << 31)) return ZKW_ERR_INVALID;
     const size_t tb = p.total_buckets();
-    const size_t max_slices = p.max_slices();
-    const size_t max_slices2 = p.max_slices2();
+    const uint32_t max_threads = (uint32_t)ctx->sm_count * ZKW_MSM_CTAS_PER_SM * kAccThreads;  // one resident wave
+    const size_t acc_threads = std::min<size_t>(max_threads, (p.max_entries() + kMinRun - 1) / kMinRun);
+    const size_t n_partials = acc_threads + tb;   // slot t + b, t < acc_threads, b < tb
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
     const size_t o_digits = take(p.max_entries() * 4);
@@ -510,10 +525,9 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     const size_t o_counts = take(tb * 4);
     const size_t o_cursor = take(tb * 4);
     const size_t o_offsets = take((tb + 1) * 4);
-    const size_t o_slices = take((tb + 1) * 4);
-    const size_t o_slices2 = take((tb + 1) * 4);
-    const size_t o_partials = take(max_slices * 128);
-    const size_t o_partials2 = take(max_slices2 * 128);
+    const size_t o_plan = take(sizeof(RunPlan));
+    const size_t o_heavy = take(tb * 4);
+    const size_t o_partials = take(n_partials * 128);
     const size_t o_buckets = take(tb * 128);
     const int lb = rowcol_lb(c);
     const uint32_t rc_per_group = (p.nb >> lb) + (1u << lb);
@@ -533,25 +547,30 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     uint32_t* counts = (uint32_t*)(ws + o_counts);
     uint32_t* cursor = (uint32_t*)(ws + o_cursor);
     uint32_t* offsets = (uint32_t*)(ws + o_offsets);
-    uint32_t* slices = (uint32_t*)(ws + o_slices);
-    uint32_t* slices2 = (uint32_t*)(ws + o_slices2);
+    RunPlan* plan = (RunPlan*)(ws + o_plan);
+    uint32_t* heavy_list = (uint32_t*)(ws + o_heavy);
     uint4* partials = (uint4*)(ws + o_partials);
-    uint4* partials2 = (uint4*)(ws + o_partials2);
     uint4* buckets = (uint4*)(ws + o_buckets);
     uint4* blocks = (uint4*)(ws + o_blocks);
     uint4* outs = (uint4*)(ws + o_out);
     ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
+    // (partial slots that no run writes - a run boundary coinciding with a bucket boundary, empty buckets - are
+    // never read either: a bucket's slot range covers exactly the runs that intersect it)
     { ProfScope ps_(ctx, "msm_recode_kernel", st); msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_scan_kernel", st); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, slices, slices2, tb); }
+    { ProfScope ps_(ctx, "msm_scan_kernel", st); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, plan, tb, (uint32_t)acc_threads); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_scatter_kernel", st); msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_accumulate_kernel", st); msm_accumulate_kernel<<<(unsigned)((max_slices + 127) / 128), 128, 0, st>>>((const uint4*)points, sorted, offsets, slices, partials, (uint32_t)tb); }
+    if (kAccSmemReserve > 0 && !ctx->msm_attr_set) {
+        ZKW_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAccSmemReserve));
+        ctx->msm_attr_set = true;
+    }
+    { ProfScope ps_(ctx, "msm_accumulate_kernel", st); msm_accumulate_kernel<<<(unsigned)((acc_threads + kAccThreads - 1) / kAccThreads), kAccThreads, kAccSmemReserve, st>>>((const uint4*)points, sorted, offsets, plan, partials, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_combine2_kernel", st); msm_combine2_kernel<<<(unsigned)((max_slices2 + 127) / 128), 128, 0, st>>>(partials, slices, slices2, partials2, (uint32_t)tb); }
+    { ProfScope ps_(ctx, "msm_combine_light_kernel", st); msm_combine_light_kernel<<<(unsigned)((tb + 127) / 128), 128, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_combine3_kernel", st); msm_combine3_kernel<<<(unsigned)((tb * 32 + 127) / 128), 128, 0, st>>>(partials2, slices2, buckets, (uint32_t)tb); }
+    { ProfScope ps_(ctx, "msm_combine_heavy_kernel", st); msm_combine_heavy_kernel<<<(unsigned)std::min<size_t>(tb, 2 * (size_t)ctx->sm_count), kHeavyThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<<<dim3((rc_per_group + kReduceThreads / 32 - 1) / (kReduceThreads / 32), p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, lb); }
     ZKW_LAUNCHED(ctx);

@@ -45,6 +45,7 @@ EXPORTS = [
     "zkw_memcpy_h2d", "zkw_memcpy_d2h", "zkw_srs_setup", "zkw_srs_get", "zkw_g1_fixed_base_mul",
     "zkw_profile_enable", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
     "zkw_keygen", "zkw_pk_destroy", "zkw_pk_info", "zkw_pk_vk", "zkw_create_proof", "zkw_create_proof_ex", "zkw_fr_to_mont", "zkw_fr_from_mont",
+    "zkw_synth_witness", "zkw_host_alloc", "zkw_host_free",
 ]
 
 
@@ -122,8 +123,33 @@ def load_library() -> C.CDLL:
     lib.zkw_ctx_destroy.restype = None
     lib.zkw_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.zkw_profile_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.zkw_synth_witness.argtypes = [C.POINTER(CircuitShape), C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(u64p), C.POINTER(C.c_size_t)]
+    lib.zkw_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+    lib.zkw_host_free.argtypes = [C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
+
+
+def witness_rows(shape: "CircuitShape") -> list[int]:
+    """cells per advice column that zkw_synth_witness fills (gate columns, then lookup-advice columns)."""
+    u = (1 << shape.k) - (shape.blinding_factors + 1)
+    return [4 * (u // 4)] * shape.num_advice + [u] * shape.num_lookup_advice
+
+
+def synth_witness(shape: "CircuitShape", lookup_bits: int, assertion: bytes, out: list[np.ndarray] | None = None) -> list[np.ndarray]:
+    """zkw_synth_witness: the synthetic circuit's advice columns (canonical uint64 cells) for `assertion`,
+    written into `out` (e.g. views of page-locked memory) or fresh arrays.  Host code, needs no GPU."""
+    lib = load_library()
+    rows = witness_rows(shape)
+    if out is None:
+        out = [np.empty(r, dtype=np.uint64) for r in rows]
+    if len(out) != len(rows) or any(o.dtype != np.uint64 or o.shape != (r,) or not o.flags.c_contiguous for o, r in zip(out, rows)):
+        raise ValueError("synth_witness: out must be C-contiguous uint64 arrays of witness_rows(shape) cells")
+    ptrs = (u64p * len(out))(*[o.ctypes.data_as(u64p) for o in out])
+    status = lib.zkw_synth_witness(C.byref(shape), C.c_uint32(lookup_bits), assertion, C.c_size_t(len(assertion)), ptrs, None)
+    if status != ZKW_OK:
+        raise ZkwError(status, "zkw_synth_witness")
+    return out
 
 
 def _strerror(status: int) -> str:
@@ -164,9 +190,13 @@ class Context:
             raise ZkwError(rc, "zkw_ctx_create")
         self.h = h
         self.device = device
+        self._host_allocs: list = []
 
     def close(self):
         if getattr(self, "h", None):
+            for p in self._host_allocs:
+                self.lib.zkw_host_free(self.h, p)
+            self._host_allocs = []
             self.lib.zkw_ctx_destroy(self.h)
             self.h = None
 
@@ -192,6 +222,13 @@ class Context:
 
     def sync(self):
         self._check(self.lib.zkw_ctx_sync(self.h), "zkw_ctx_sync")
+
+    def host_array(self, count: int) -> np.ndarray:
+        """(count,) uint64 array in page-locked host memory (freed with the context)."""
+        p = C.c_void_p()
+        self._check(self.lib.zkw_host_alloc(self.h, C.c_size_t(8 * max(count, 1)), C.byref(p)), "zkw_host_alloc")
+        self._host_allocs.append(p)
+        return np.ctypeslib.as_array(C.cast(p, u64p), shape=(max(count, 1),))[:count]
 
     def msm_config(self, window_bits: int = 0, precompute: bool = True):
         self._check(self.lib.zkw_msm_config(self.h, window_bits, int(precompute)), "zkw_msm_config")

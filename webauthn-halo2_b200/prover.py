@@ -136,15 +136,21 @@ class ProverState:
         self.ctx.srs_setup(params.degree, tau)                       # gen_srs(degree)
         fixed = [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.fixed_columns()]
         self.pk = keygen(self.ctx, self.shape, fixed, self.circuit.permutation_mapping(), self.circuit)   # keygen_vk + keygen_pk
+        self._staging = None
 
     def synthesize(self, assertion: bytes) -> list[np.ndarray]:
         return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
 
     def prove(self, assertion: bytes, transcript: int, seed: int | None = None, shplonk: bool = False) -> bytes:
-        """witness synthesis on the host, one H2D copy of the canonical advice values, proof bytes back."""
+        """witness synthesis on the host (zkw_synth_witness, into page-locked staging columns owned by this
+        state), one H2D copy of the canonical advice values, proof bytes back."""
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
-        cols = self.circuit.synthesize(assertion)          # canonical values < 2^64: shipped as one u64 per row
+        if self._staging is None:
+            self._staging = [self.ctx.host_array(r) for r in native.witness_rows(self.shape)]
+        # canonical values < 2^64: shipped as one u64 per row; create_proof returns after the device is done
+        # with the staging columns (the proof bytes depend on them), so the next call may overwrite them
+        cols = native.synth_witness(self.shape, self.params.lookup_bits, assertion, out=self._staging)
         return create_proof(self.ctx, self.pk, cols, seed, transcript, shplonk=shplonk, u64=True)
 
     def close(self):
