@@ -240,6 +240,7 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->twiddles) free_buffer(kv.second);
+    for (auto& kv : ctx->staged_twiddles) free_buffer(kv.second);
     free_buffer(ctx->ntt_scratch); free_buffer(ctx->ntt_scratch_aux); free_buffer(ctx->msm_ws);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
@@ -271,7 +272,7 @@ const char* zkw_last_cuda_error(zkw_ctx* ctx) { return ctx ? ctx->last_err.c_str
 uint64_t zkw_ctx_launch_count(zkw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute) {
-    if (!ctx || window_bits < 0 || window_bits > 20 || window_bits == 1) return ZKW_ERR_INVALID;
+    if (!ctx || window_bits < 0 || window_bits > 24 || window_bits == 1) return ZKW_ERR_INVALID;
     ctx->msm_window_bits = window_bits;
     ctx->msm_precompute = precompute ? 1 : 0;
     return ZKW_OK;

@@ -20,6 +20,17 @@ struct TwiddleKey {
     }
 };
 
+struct StagedTwiddleKey {
+    std::array<uint64_t, 4> omega;
+    unsigned log_n, s0, B;
+    bool operator<(const StagedTwiddleKey& o) const {
+        if (log_n != o.log_n) return log_n < o.log_n;
+        if (s0 != o.s0) return s0 < o.s0;
+        if (B != o.B) return B < o.B;
+        return omega < o.omega;
+    }
+};
+
 struct DeviceBuffer {
     void* ptr = nullptr;
     size_t bytes = 0;
@@ -47,10 +58,13 @@ struct zkw_ctx {
     // MSM tuning: window bits (0 = automatic) and whether fixed bases get window tables
     int msm_window_bits = 0;
     int msm_precompute = 1;
+    bool ntt_attr_set = false;           // NTT pass kernel's dynamic shared memory opt-in done
     bool msm_attr_set = false;           // accumulate kernel's dynamic shared memory opt-in done
 
     // twiddle tables: omega^i for i < 2^(log_n-1), keyed by (omega, log_n)
     std::map<zkw::TwiddleKey, zkw::DeviceBuffer> twiddles;
+    // per-(omega, log_n, pass) compact copies of a pass's last-stage twiddles, laid out for one bulk copy per tile
+    std::map<zkw::StagedTwiddleKey, zkw::DeviceBuffer> staged_twiddles;
     // reusable scratch areas (grown on demand, never shrunk)
     zkw::DeviceBuffer ntt_scratch, ntt_scratch_aux;
     cudaStream_t aux_stream = nullptr;   // prover: transforms that overlap the main stream's MSMs

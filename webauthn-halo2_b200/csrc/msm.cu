@@ -417,10 +417,13 @@ int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint
 
 static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
     if (ctx->msm_window_bits > 0) return ctx->msm_window_bits;
-    // larger windows pay off once the bucket-side work (~2^(c-1) * c / 2 additions) is small against the
-    // N * ceil(255 / c) mixed additions of the accumulation
+    // What matters is the window COUNT ceil(255 / c): the narrowest c of each count wins (fewest buckets for the same
+    // number of additions).  Measured on B200 (tools/window_sweep_large.py, ms per uniform MSM):
+    //   2^20: c=16 3.56, c=17 3.30, c=20 3.76      2^21: c=16 6.82, c=17 6.23, c=20 6.39
+    //   2^22: c=17 12.2, c=20 11.6, c=22 14.0      2^24: c=17 48.7, c=20 43.1, c=22 46.1
+    //   2^19: c=16 2.02, c=17 2.01 (a tie; 16 keeps the tables' 16 windows)
     if (n >= (1u << 22)) return 20;
-    if (n >= (1u << 21)) return 19;
+    if (n >= (1u << 20)) return 17;
     return n >= (1u << 13) ? 16 : 8;
 }
 

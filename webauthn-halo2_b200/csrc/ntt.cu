@@ -17,16 +17,47 @@
 //
 // The kernel is integer-ALU bound (one 254-bit Montgomery product per butterfly), not HBM bound;
 // see DESIGN.md for the roofline.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
 #include "common.cuh"
 
 namespace zkw {
 
-constexpr int kTileLog = 10;
-constexpr int kNttThreads = 128;
-constexpr int kMaxPassBits = 7;
+#ifndef ZKW_NTT_TILE_LOG
+#define ZKW_NTT_TILE_LOG 10
+#endif
+#ifndef ZKW_NTT_THREADS
+#define ZKW_NTT_THREADS 128
+#endif
+#ifndef ZKW_NTT_MAX_PASS_BITS
+#define ZKW_NTT_MAX_PASS_BITS 7
+#endif
 #ifndef ZKW_NTT_MIN_BLOCKS
 #define ZKW_NTT_MIN_BLOCKS 4
 #endif
+constexpr int kTileLog = ZKW_NTT_TILE_LOG;
+constexpr int kNttThreads = ZKW_NTT_THREADS;
+constexpr int kMaxPassBits = ZKW_NTT_MAX_PASS_BITS;
+// two uint4 planes of one tile + the staged last-stage twiddles (half a tile of elements) + one mbarrier
+constexpr size_t kNttSmemBytes = ((size_t)3 * sizeof(uint4) << kTileLog) + 16;
+
+// ---- TMA (bulk asynchronous copy) plumbing: one elected thread arms an mbarrier with the byte count and issues
+// cp.async.bulk global -> shared; every thread later waits on the barrier's phase 0 ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
 
 struct NttPassArgs {
     const uint4* src;
@@ -42,6 +73,8 @@ struct NttPassArgs {
     int scale;       // last pass: multiply output element i by scale3[i mod 3]
     Fr zeta, zeta2;
     Fr scale3[3];
+    const uint4* stw;   // staged twiddles of this pass's LAST stage, one contiguous block per tile group, or nullptr
+    unsigned stw_group_mask;  // tile -> group = tile & mask
 };
 
 __device__ __forceinline__ Fr lds_fr(const uint4* lo, const uint4* hi, int p) {
@@ -57,8 +90,11 @@ __device__ __forceinline__ void sts_fr(uint4* lo, uint4* hi, int p, const Fr& v)
 }
 
 // R butterfly stages on 2^R register-resident elements per task.
+// tlo / thi: the staged twiddles of the pass's last stage (entry (j << C) + cc, j = butterfly index inside the
+// stage), or nullptr when this round does not contain that stage / nothing is staged.
 template <int R>
-__device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassArgs& a, unsigned tile, int t) {
+__device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassArgs& a, unsigned tile, int t,
+                                          const uint4* tlo, const uint4* thi) {
     const int C = a.tl - a.B;
     const int ntasks = 1 << (a.tl - R);
     const int s = a.s0 + t;
@@ -89,7 +125,9 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
 #else
                     const unsigned idx = (jm + (el << s)) << sh;
 #endif
-                    Fr w = Fr::load_nc(a.tw + 2 * (size_t)idx);
+                    Fr w;
+                    if (u == R - 1 && tlo) w = lds_fr(tlo, thi, (int)((((unsigned)glow | (el << t)) << C) + cc));
+                    else w = Fr::load_nc(a.tw + 2 * (size_t)idx);
                     tv = x[e | (1 << u)] * w;
                 }
                 Fr uu = x[e];
@@ -103,11 +141,22 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
 }
 
 __global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kernel(const NttPassArgs a) {
-    __shared__ uint4 slo[1 << kTileLog];
-    __shared__ uint4 shi[1 << kTileLog];
+    extern __shared__ uint4 ntt_smem[];
+    uint4* slo = ntt_smem;
+    uint4* shi = ntt_smem + (1 << kTileLog);
+    uint4* tlo = ntt_smem + (2 << kTileLog);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(ntt_smem + (3 << kTileLog));
     const unsigned tile = blockIdx.x;
     const int C = a.tl - a.B;
     const int tsize = 1 << a.tl;
+    // ---- stage the last stage's twiddles: one bulk copy, in flight while the tile is gathered and the
+    // earlier rounds run ----
+    const int stw_entries = 1 << (a.tl - 1);   // 2^(B-1) butterflies x 2^C columns
+    const uint4* thi = tlo + stw_entries;
+    if (a.stw && threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        bulk_load(tlo, a.stw + 2 * (size_t)(tile & a.stw_group_mask) * stw_entries, (uint32_t)stw_entries * 32u, bar);
+    }
     // ---- gather the tile ----
     for (int q = threadIdx.x; q < tsize; q += kNttThreads) {
         int mid, cc;
@@ -138,9 +187,12 @@ __global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kern
     int t = 0;
     while (t < a.B) {
         const int r = (a.B - t >= 3) ? 3 : (a.B - t);
-        if (r == 3) ntt_round<3>(slo, shi, a, tile, t);
-        else if (r == 2) ntt_round<2>(slo, shi, a, tile, t);
-        else ntt_round<1>(slo, shi, a, tile, t);
+        const bool last = t + r == a.B;
+        if (last && a.stw) mbar_wait(bar, 0);   // the barrier was initialised before the __syncthreads above
+        const uint4* wl = (last && a.stw) ? tlo : nullptr;
+        if (r == 3) ntt_round<3>(slo, shi, a, tile, t, wl, thi);
+        else if (r == 2) ntt_round<2>(slo, shi, a, tile, t, wl, thi);
+        else ntt_round<1>(slo, shi, a, tile, t, wl, thi);
         t += r;
         __syncthreads();
     }
@@ -168,6 +220,49 @@ __global__ void twiddle_kernel(uint4* tw, Fr omega, unsigned count, unsigned run
         w.store(tw + 2 * (size_t)i);
         w = w * omega;
     }
+}
+
+// Compact copy of the twiddles a pass's last stage needs, laid out the way a tile consumes them: for tile
+// group q (the tile's low column bits), the block [q] holds plane 0 (low 16 bytes) of entries (j << C) + cc,
+// then plane 1 - so that ONE contiguous bulk copy stages a tile's 2^(tl-1) twiddles into shared memory.
+// entry (q, j, cc) = omega^(((j << s0) | (q << C) | cc) << (log_n - s0 - B)).
+__global__ void stage_twiddle_kernel(const uint4* __restrict__ tw, uint4* __restrict__ out, int log_n, int s0, int B, int C, unsigned groups) {
+    const unsigned per = 1u << (B - 1 + C);
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)groups * per) return;
+    const unsigned q = (unsigned)(i / per), e = (unsigned)(i % per);
+    const unsigned cc = e & ((1u << C) - 1u), j = e >> C;
+    const size_t idx = (size_t)(((j << s0) | (q << C) | cc)) << (log_n - s0 - B);
+    out[2 * (size_t)q * per + e] = tw[2 * idx];
+    out[2 * (size_t)q * per + per + e] = tw[2 * idx + 1];
+}
+
+static int ntt_get_staged(zkw_ctx* ctx, const uint64_t omega[4], const uint64_t* tw, int log_n, int s0, int B, int C,
+                          const uint64_t** out_dev, unsigned* group_mask) {
+    *out_dev = nullptr;
+    *group_mask = 0;
+    if (s0 < C || s0 == 0 || B < 1) return ZKW_OK;         // first pass: 2^(B-1) twiddles shared by every tile, L1 keeps them
+    const unsigned groups = 1u << (s0 - C);
+    const size_t bytes = (size_t)groups * ((size_t)32 << (B - 1 + C));
+    if (bytes > ((size_t)1 << 30)) return ZKW_OK;          // huge transforms: plain loads
+    StagedTwiddleKey key;
+    memcpy(key.omega.data(), omega, 32);
+    key.log_n = (unsigned)log_n; key.s0 = (unsigned)s0; key.B = (unsigned)B;
+    auto it = ctx->staged_twiddles.find(key);
+    if (it == ctx->staged_twiddles.end()) {
+        DeviceBuffer buf;
+        ZKW_TRY(ensure_buffer(ctx, buf, bytes));
+        const size_t total = (size_t)groups << (B - 1 + C);
+        // built on the context's main stream, like the main table; a transform on another stream that needs it
+        // right away is ordered by the synchronisation below (first use only)
+        { ProfScope ps_(ctx, "stage_twiddle_kernel"); stage_twiddle_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint4*)tw, (uint4*)buf.ptr, log_n, s0, B, C, groups); }
+        ZKW_LAUNCHED(ctx);
+        ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        it = ctx->staged_twiddles.emplace(key, buf).first;
+    }
+    *out_dev = (const uint64_t*)it->second.ptr;
+    *group_mask = groups - 1;
+    return ZKW_OK;
 }
 
 // n == 1 or scaling-only helper: dst[i] = src[i] * scale3[i mod 3]
@@ -226,8 +321,35 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     }
     const uint64_t* tw = nullptr;
     ZKW_TRY(ntt_get_twiddles(ctx, omega, log_n, &tw));
-    const int npass = (int)((log_n + kMaxPassBits - 1) / kMaxPassBits);
-    const int base = (int)log_n / npass, rem = (int)log_n % npass;
+    if (kNttSmemBytes > 48 * 1024 && !ctx->ntt_attr_set) {
+        ZKW_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttSmemBytes));
+        ctx->ntt_attr_set = true;
+    }
+    // stages per pass: as even as possible with at most kMaxPassBits each; ZKW_NTT_PLAN_<log_n>="9,6,6" overrides
+    // the split (tuning aid: each entry <= the tile's log size, entries sum to log_n)
+    std::vector<int> plan;
+    {
+        const int np = (int)((log_n + kMaxPassBits - 1) / kMaxPassBits);
+        const int base = (int)log_n / np, rem = (int)log_n % np;
+        for (int p = 0; p < np; p++) plan.push_back(base + (p < rem ? 1 : 0));
+        char name[32];
+        snprintf(name, sizeof(name), "ZKW_NTT_PLAN_%u", log_n);
+        if (const char* env = getenv(name)) {
+            std::vector<int> alt;
+            int sum = 0;
+            bool ok = true;
+            for (const char* q = env; *q;) {
+                char* end = nullptr;
+                const long v = strtol(q, &end, 10);
+                if (end == q || v < 1 || v > (long)(log_n < (unsigned)kTileLog ? log_n : kTileLog)) { ok = false; break; }
+                alt.push_back((int)v);
+                sum += (int)v;
+                q = *end == ',' ? end + 1 : end;
+            }
+            if (ok && sum == (int)log_n) plan = alt;
+        }
+    }
+    const int npass = (int)plan.size();
     // The first pass permutes (bit reversal), so it cannot run in place when there are several
     // tiles: route it through the scratch buffer unless src and dst already differ.
     const bool in_place = (const void*)src_dev == (const void*)dst_dev;
@@ -258,7 +380,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     int s0 = 0;
     const uint64_t* cur_src = src_dev;
     for (int p = 0; p < npass; p++) {
-        const int B = base + (p < rem ? 1 : 0);
+        const int B = plan[p];
         a.s0 = s0;
         a.B = B;
         a.first = (p == 0);
@@ -269,8 +391,17 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         if (p == 0 && tmp && npass == 1) out = tmp;            // cannot happen (npass==1 => log_n<=7), kept for clarity
         a.src = (const uint4*)cur_src;
         a.dst = (uint4*)out;
+        a.stw = nullptr;
+        a.stw_group_mask = 0;
+#ifndef ZKW_NTT_NO_STAGE
+        if (a.tl == kTileLog) {
+            const uint64_t* stw = nullptr;
+            ZKW_TRY(ntt_get_staged(ctx, omega, tw, (int)log_n, s0, B, a.tl - B, &stw, &a.stw_group_mask));
+            a.stw = (const uint4*)stw;
+        }
+#endif
         const unsigned tiles = (unsigned)(n >> a.tl);
-        { ProfScope ps_(ctx, "ntt_pass_kernel", st); ntt_pass_kernel<<<tiles, kNttThreads, 0, st>>>(a); }
+        { ProfScope ps_(ctx, "ntt_pass_kernel", st); ntt_pass_kernel<<<tiles, kNttThreads, kNttSmemBytes, st>>>(a); }
         ZKW_LAUNCHED(ctx);
         cur_src = out;
         s0 += B;
