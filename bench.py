@@ -389,8 +389,8 @@ def run_b200(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": state.h2d,
                "d2h_bytes_per_step": len(state.proof), "steps": e2e_steps,
-               "path": "generate_proof_evm mirror (ProverState.prove): assertion bytes -> host witness synthesis -> one H2D copy of the "
-                       "advice column -> zkw_create_proof_ex -> proof bytes"}
+               "path": "generate_proof_evm mirror (ProverState.prove): assertion bytes -> host witness synthesis (zkw_synth_witness into "
+                       "page-locked staging) -> one H2D copy of the advice column -> zkw_create_proof_ex -> proof bytes"}
     elif not args.no_e2e:
         host = HostAbiProof(zkw, ctx, torch, state)
         host.step()
@@ -465,7 +465,7 @@ def run_b200(args):
         roofline = {
             "kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": (achieved / pk["hbm_gbs"]) if achieved else None,
-            "traffic": 1.0666e9, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one uniform-scalar launch (profiles/r1b_prof_msm_acc_b_raw.csv)",
+            "traffic": 1.0575e9, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one uniform-scalar launch (profiles/r1c_prof_msm_acc_raw.csv, summary in profiles/r1c_ncu_summary.md)",
             "peak_source": pk_src + " copy bandwidth (MEASURED_PEAKS.json)",
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms, "launches": acc_cnt,
             "share_of_kernel_time": (acc_ms / total_kernel_ms) if total_kernel_ms else None,

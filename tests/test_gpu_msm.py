@@ -97,6 +97,37 @@ def test_msm_resident_srs_with_window_tables(zkw, oracle, n):
         c.close()
 
 
+@pytest.mark.parametrize("kind", ["all_equal", "plus_minus_one", "sorted_small", "half_zero", "two_values", "run_aligned"])
+def test_msm_skewed_scalars_over_window_tables(zkw, oracle, kind):
+    """Witness-shaped scalar vectors put most entries into a handful of buckets: the equal-run accumulation
+    cuts those buckets into thousands of partials (slots t + b) that the queued heavy-bucket kernel folds."""
+    from oracle import pyref as pr
+    n = 1 << 15
+    rng = np.random.default_rng(7)
+    if kind == "all_equal":
+        vals = [0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF] * n
+    elif kind == "plus_minus_one":
+        vals = [1 if i % 3 else pr.R - 1 for i in range(n)]
+    elif kind == "sorted_small":
+        vals = sorted(int(x) for x in rng.integers(0, 1 << 18, n))          # a permuted lookup column
+    elif kind == "half_zero":
+        vals = [0 if i % 2 else int(x) for i, x in enumerate(rng.integers(0, 1 << 62, n))]
+    elif kind == "two_values":
+        vals = [(1 << 200) + 5 if i < n // 3 else (1 << 16) - 1 for i in range(n)]   # digit 2^16 - 1 recodes to -1 with a carry
+    else:
+        vals = [(i // 16) + 1 for i in range(n)]                             # runs of 16 equal digits: run and bucket boundaries coincide
+    s = oracle.fr_to_mont(vals)
+    g = _bases(oracle, n, 77)
+    want = _affine(oracle, oracle.best_multiexp(s, g))
+    c = zkw.Context(0)
+    try:
+        c.srs_load(g, None)
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], want)
+        assert np.array_equal(c.msm(s, g)[:8], want)      # caller bases: one bucket set per window
+    finally:
+        c.close()
+
+
 def test_msm_before_srs_load_is_an_error(zkw, oracle):
     c = zkw.Context(0)
     try:
@@ -107,7 +138,7 @@ def test_msm_before_srs_load_is_an_error(zkw, oracle):
         c.close()
 
 
-@pytest.mark.parametrize("c_bits", [4, 7, 11, 13, 16, 19, 20])
+@pytest.mark.parametrize("c_bits", [4, 7, 11, 13, 16, 17, 19, 20, 22])
 def test_msm_window_sizes(zkw, oracle, c_bits):
     c = zkw.Context(0)
     try:

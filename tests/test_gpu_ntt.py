@@ -25,6 +25,19 @@ def test_ntt_matches_oracle(ctx, oracle, log_n):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("log_n,plan", [(16, "8,8"), (16, "10,6"), (16, "6,10"), (16, "3,3,10"), (16, "4,4,4,4"), (18, "9,9"), (18, "7,7,4"),
+                                        (18, "1,7,10"), (13, "10,3"), (13, "3,10"), (12, "6,6")])
+def test_ntt_stage_splits_and_staged_twiddles(ctx, oracle, monkeypatch, log_n, plan):
+    """Every split of the log_n stages into passes gives the same transform.  Passes after the first take their
+    last stage's twiddles from the per-(pass, tile group) table that one TMA bulk copy stages into shared memory
+    (any s0 >= C, including C = 0 where a tile is a single column)."""
+    monkeypatch.setenv(f"ZKW_NTT_PLAN_{log_n}", plan)
+    n = 1 << log_n
+    a = oracle.fr_random(n, 300 + log_n)
+    _, om = _omega(oracle, log_n)
+    assert np.array_equal(ctx.ntt(a, om), oracle.best_fft(a, om))
+
+
 @pytest.mark.parametrize("log_n", [1, 5, 10, 12, 17])
 def test_inverse_ntt_with_scale(ctx, oracle, log_n):
     from oracle import pyref as pr
