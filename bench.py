@@ -515,10 +515,18 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
+    # first collective), so file descriptor 1 is pointed at stderr for the whole run and the JSON line alone goes
+    # to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
