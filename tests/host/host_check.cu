@@ -4,6 +4,7 @@
 #include <cstring>
 #include <vector>
 #include "curve.cuh"
+#include "inverse.cuh"
 #include "../../oracle/zkw_oracle.h"
 using namespace zkw;
 
@@ -75,6 +76,28 @@ int main() {
         CHECK(!memcmp(g, o, 64), "xyzz add equal -> dbl");
         G1Xyzz e = G1Xyzz::identity(); e.add(t2); e.add(G1Xyzz::identity());
         affine_of(e, g); affine_of(t2, o); CHECK(!memcmp(g, o, 64), "identity handling");
+    }
+    // binary-GCD inversion (inverse.cuh) against the oracle's inversion: random elements and the edge cases of the
+    // divstep loop (0, 1, -1, 2, single bits in every limb, values just below the modulus)
+    {
+        const int M2 = 3000;
+        std::vector<uint64_t> v(4 * M2);
+        zko_fr_random(v.data(), M2, 99);
+        for (int i = 0; i < M2; i++) {
+            uint64_t r[4];
+            Fr x = from_u64<Fr>(&v[4 * i]);
+            Fq y = from_u64<Fq>(&v[4 * i]);
+            if (i == 0) { x = Fr::zero(); y = Fq::zero(); }
+            if (i == 1) { x = Fr::one(); y = Fq::one(); }
+            if (i == 2) { x = Fr::zero() - Fr::one(); y = Fq::zero() - Fq::one(); }
+            if (i == 3) { x = Fr::one() + Fr::one(); y = Fq::one() + Fq::one(); }
+            if (i >= 4 && i < 36) { x = Fr::zero(); x.l[(i - 4) / 4] = 1u << ((i * 7) % 32); y = Fq::zero(); y.l[(i - 4) / 4] = 1u << ((i * 11) % 32); }
+            if (i >= 36 && i < 44) { x = Fr::zero() - from_u64<Fr>(&v[4 * i]).from_mont().from_mont(); x = Fr::zero() - Fr::one() - Fr::one(); x.l[0] -= (i - 36); y = Fq::zero() - Fq::one(); y.l[0] -= (i - 36); }
+            Fr xi = fp_inv_bingcd(x);
+            zko_fr_inv(r, (const uint64_t*)x.l); CHECK(!memcmp(xi.l, r, 32), "fr bingcd inv %d", i);
+            Fq yi = fp_inv_bingcd(y);
+            zko_fq_inv(r, (const uint64_t*)y.l); CHECK(!memcmp(yi.l, r, 32), "fq bingcd inv %d", i);
+        }
     }
     printf(fails ? "HOST_CHECK FAILED (%d)\n" : "HOST_CHECK OK\n", fails);
     return fails ? 1 : 0;
