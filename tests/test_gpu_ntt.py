@@ -27,11 +27,14 @@ def test_ntt_matches_oracle(ctx, oracle, log_n):
 
 @pytest.mark.parametrize("log_n,plan", [(16, "8,8"), (16, "10,6"), (16, "6,10"), (16, "3,3,10"), (16, "4,4,4,4"), (18, "9,9"), (18, "7,7,4"),
                                         (18, "1,7,10"), (13, "10,3"), (13, "3,10"), (12, "6,6")])
-def test_ntt_stage_splits_and_staged_twiddles(ctx, oracle, monkeypatch, log_n, plan):
-    """Every split of the log_n stages into passes gives the same transform.  Passes after the first take their
-    last stage's twiddles from the per-(pass, tile group) table that one TMA bulk copy stages into shared memory
-    (any s0 >= C, including C = 0 where a tile is a single column)."""
+@pytest.mark.parametrize("staged", ["0", "1"])
+def test_ntt_stage_splits_and_staged_twiddles(ctx, oracle, monkeypatch, log_n, plan, staged):
+    """Every split of the log_n stages into passes gives the same transform, with and without the opt-in TMA path
+    (ZKW_NTT_STAGE_TWIDDLES=1): passes after the first then take their last stage's twiddles from the per-(pass,
+    tile group) table that one bulk copy stages into shared memory (any s0 >= C, including C = 0 where a tile is
+    a single column)."""
     monkeypatch.setenv(f"ZKW_NTT_PLAN_{log_n}", plan)
+    monkeypatch.setenv("ZKW_NTT_STAGE_TWIDDLES", staged)
     n = 1 << log_n
     a = oracle.fr_random(n, 300 + log_n)
     _, om = _omega(oracle, log_n)

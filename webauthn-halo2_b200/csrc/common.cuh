@@ -160,6 +160,26 @@ int fixed_base_mul_dev(zkw_ctx* ctx, const uint64_t* scalars_dev, size_t n, uint
 // quotient.cu
 int quotient_run(zkw_ctx* ctx, const zkw_quotient_inputs* in /* device vectors */, uint64_t* h_ext_dev);
 
+#ifdef __CUDACC__
+// ---- TMA (bulk asynchronous copy) plumbing, used by ntt.cu (twiddle staging): one
+// elected thread arms an mbarrier with the byte count and issues cp.async.bulk global -> shared; the consumers wait
+// on the barrier's phase ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+#endif
+
 // domain constants (host side, Montgomery form), see domain.cpp
 struct DomainConsts {
     unsigned k, ext_k;

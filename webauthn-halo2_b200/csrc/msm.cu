@@ -22,7 +22,7 @@
 //              range follows from the bucket's offsets alone).  The next affine point is prefetched (two
 //              128-bit loads per coordinate) while the current one is added.
 //   combine    one thread per bucket folds its (typically 3-4) partials; buckets cut into more than
-//              kLight runs (skewed scalars) get one warp each: strided loop + shuffle tree.
+//              kLight runs (skewed scalars) are queued and get one CTA each: strided loop + shuffle tree.
 //   reduce     sum_b b * B_b by rows and columns of the bucket index (b - 1 = hi * 2^lb + lo): tree sums of
 //              every row and column, then two short bit-sliced weighted sums; the final ~2c-step Horner
 //              runs on the host in microseconds instead of as a latency-bound chain on the device.
@@ -48,7 +48,7 @@ namespace zkw {
 constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
 constexpr int kAccThreads = 128;
 constexpr int kMinRun = 16;        // shortest run worth a thread (small MSMs use fewer threads instead)
-constexpr int kLight = 8;          // partials per bucket folded by one thread; more -> one warp
+constexpr int kLight = 8;          // partials per bucket folded by one thread; more -> queued for a CTA
 constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
 struct MsmPlan {

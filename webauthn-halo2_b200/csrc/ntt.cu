@@ -39,25 +39,10 @@ namespace zkw {
 constexpr int kTileLog = ZKW_NTT_TILE_LOG;
 constexpr int kNttThreads = ZKW_NTT_THREADS;
 constexpr int kMaxPassBits = ZKW_NTT_MAX_PASS_BITS;
-// two uint4 planes of one tile + the staged last-stage twiddles (half a tile of elements) + one mbarrier
+// two uint4 planes of one tile; with twiddle staging also the last stage's twiddles (half a tile of elements) and
+// one mbarrier
+constexpr size_t kNttTileBytes = (size_t)2 * sizeof(uint4) << kTileLog;
 constexpr size_t kNttSmemBytes = ((size_t)3 * sizeof(uint4) << kTileLog) + 16;
-
-// ---- TMA (bulk asynchronous copy) plumbing: one elected thread arms an mbarrier with the byte count and issues
-// cp.async.bulk global -> shared; every thread later waits on the barrier's phase 0 ---------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-                 ::"r"(smem_u32(bar)), "r"(phase) : "memory");
-}
 
 struct NttPassArgs {
     const uint4* src;
@@ -321,7 +306,15 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     }
     const uint64_t* tw = nullptr;
     ZKW_TRY(ntt_get_twiddles(ctx, omega, log_n, &tw));
-    if (kNttSmemBytes > 48 * 1024 && !ctx->ntt_attr_set) {
+    // Twiddle staging by TMA is OFF unless ZKW_NTT_STAGE_TWIDDLES=1.  Measured (profiles/r1c_ntt_tuning.md): against
+    // the same kernel without staging it gains 1.5-2 %, but its 16 KB per CTA lift four resident CTAs from 132 KB to
+    // 196+ KB of shared memory, the SM's carve-out goes to 228 KB, and the L1 left over for this kernel's early-stage
+    // twiddles and for the MSM kernels running next to it shrinks from 96 KB to nothing: the k = 19 proof takes
+    // 27.6-27.8 ms with the 48 KB kernel (staged or not) against 27.2-27.3 ms with the 32 KB one.
+    const char* stage_env = getenv("ZKW_NTT_STAGE_TWIDDLES");
+    const bool stage = stage_env && stage_env[0] == '1';
+    const size_t smem_bytes = stage ? kNttSmemBytes : kNttTileBytes;
+    if (smem_bytes > 48 * 1024 && !ctx->ntt_attr_set) {
         ZKW_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNttSmemBytes));
         ctx->ntt_attr_set = true;
     }
@@ -393,15 +386,13 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         a.dst = (uint4*)out;
         a.stw = nullptr;
         a.stw_group_mask = 0;
-#ifndef ZKW_NTT_NO_STAGE
-        if (a.tl == kTileLog) {
+        if (stage && a.tl == kTileLog) {
             const uint64_t* stw = nullptr;
             ZKW_TRY(ntt_get_staged(ctx, omega, tw, (int)log_n, s0, B, a.tl - B, &stw, &a.stw_group_mask));
             a.stw = (const uint4*)stw;
         }
-#endif
         const unsigned tiles = (unsigned)(n >> a.tl);
-        { ProfScope ps_(ctx, "ntt_pass_kernel", st); ntt_pass_kernel<<<tiles, kNttThreads, kNttSmemBytes, st>>>(a); }
+        { ProfScope ps_(ctx, "ntt_pass_kernel", st); ntt_pass_kernel<<<tiles, kNttThreads, smem_bytes, st>>>(a); }
         ZKW_LAUNCHED(ctx);
         cur_src = out;
         s0 += B;
