@@ -46,9 +46,17 @@ namespace zkw {
 #define ZKW_MSM_SMEM_RESERVE 0
 #endif
 constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
+// Accumulate grid in resident waves.  One wave gives the longest runs and the fewest partials, but its CTAs live for
+// the whole kernel: any slot another stream's kernel holds when the grid launches pushes accumulate CTAs into a
+// second, nearly empty wave.  With W waves the runs are W times shorter and that tail is bounded by 1/W of the kernel.
+// Measured (tools/msm_ab.py, same call): W = 1 / 2 / 3 / 4 -> uniform MSM 1.955 / 1.93 / 1.92 / 1.93 ms, k = 19 proof
+// 27.38 / 27.47 / 27.46 / 27.75 ms: the proof is multiplier-bound either way, one wave keeps the partials fewest.
+#ifndef ZKW_MSM_WAVES
+#define ZKW_MSM_WAVES 1
+#endif
 constexpr int kAccThreads = 128;
 constexpr int kMinRun = 16;        // shortest run worth a thread (small MSMs use fewer threads instead)
-constexpr int kLight = 8;          // partials per bucket folded by one thread; more -> queued for a CTA
+constexpr int kLight = ZKW_MSM_WAVES > 1 ? 16 : 8;          // partials per bucket folded by one thread; more -> queued for a CTA
 constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
 struct MsmPlan {
@@ -518,7 +526,7 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     make_plan(p, n, c, table);
     if (p.max_entries() >= (1ull << 31)) return ZKW_ERR_INVALID;
     const size_t tb = p.total_buckets();
-    const uint32_t max_threads = (uint32_t)ctx->sm_count * ZKW_MSM_CTAS_PER_SM * kAccThreads;  // one resident wave
+    const uint32_t max_threads = (uint32_t)ctx->sm_count * ZKW_MSM_CTAS_PER_SM * kAccThreads * ZKW_MSM_WAVES;  // whole resident waves
     const size_t acc_threads = std::min<size_t>(max_threads, (p.max_entries() + kMinRun - 1) / kMinRun);
     const size_t n_partials = acc_threads + tb;   // slot t + b, t < acc_threads, b < tb
     size_t off = 0;
