@@ -510,7 +510,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--k", type=int, default=K)
     ap.add_argument("--workload", default="proof", choices=["proof", "hotpath"])
-    ap.add_argument("--batch", type=int, default=16, help="proofs in the batch-throughput leg (0 = skip)")
+    ap.add_argument("--batch", type=int, default=64, help="proofs per GPU in the batch-throughput leg: BASELINE configs[2] (64 on one GPU) and [3] (512 over 8); 0 = skip")
     ap.add_argument("--workers", type=int, default=3, help="concurrent provers per GPU in the batch leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -55,7 +55,10 @@ constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
 #define ZKW_MSM_WAVES 1
 #endif
 constexpr int kAccThreads = 128;
-constexpr int kMinRun = 16;        // shortest run worth a thread (small MSMs use fewer threads instead)
+#ifndef ZKW_MSM_MIN_RUN
+#define ZKW_MSM_MIN_RUN 16
+#endif
+constexpr int kMinRun = ZKW_MSM_MIN_RUN;        // shortest run worth a thread (small MSMs use fewer threads instead)
 constexpr int kLight = ZKW_MSM_WAVES > 1 ? 16 : 8;          // partials per bucket folded by one thread; more -> queued for a CTA
 constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
