@@ -8,6 +8,7 @@
 #include <array>
 #include "../../include/zkw_b200.h"
 #include "curve.cuh"
+#include "inverse.cuh"
 
 namespace zkw {
 

@@ -249,20 +249,32 @@ struct Fp {
     // Montgomery product a*b*R^-1 mod m, fully reduced.
     __host__ __device__ __forceinline__ friend Fp operator*(const Fp& a, const Fp& b) {
 #ifndef __CUDA_ARCH__
-        // portable word-serial Montgomery product (host-side unit tests of the device formulas)
-        uint32_t t[10] = {0};
-        for (int i = 0; i < 8; i++) {
-            uint64_t c = 0;
-            for (int j = 0; j < 8; j++) { c += (uint64_t)a.l[j] * b.l[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
-            c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
-            uint32_t m = t[0] * P::INV;
-            c = (uint64_t)m * P::mod(0) + t[0]; c >>= 32;
-            for (int j = 1; j < 8; j++) { c += (uint64_t)m * P::mod(j) + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
-            c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
+        // host path: word-serial (CIOS) Montgomery product over four 64-bit limbs with 128-bit partial products.
+        // The host runs the last ~2c point operations and one inversion of every MSM and the transcript-side
+        // field arithmetic of the prover, between the device's rounds - it is on the proof's critical path.
+        typedef unsigned __int128 u128;
+        uint64_t x[4], y[4], md[4];
+        for (int i = 0; i < 4; i++) {
+            x[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+            y[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
+            md[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+        }
+        // -m^-1 mod 2^64 from the 32-bit constant: one Newton step on m^-1 mod 2^32
+        const uint64_t minv32 = (uint32_t)(0u - P::INV);
+        const uint64_t inv64 = 0 - minv32 * (2 - md[0] * minv32);
+        uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < 4; i++) {
+            u128 c = 0;
+            for (int j = 0; j < 4; j++) { c += (u128)x[j] * y[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+            const uint64_t m = t[0] * inv64;
+            c = (u128)m * md[0] + t[0]; c >>= 64;
+            for (int j = 1; j < 4; j++) { c += (u128)m * md[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+            c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
         }
         Fp r;
-        for (int i = 0; i < 8; i++) r.l[i] = t[i];
-        r.reduce_once();
+        for (int i = 0; i < 4; i++) { r.l[2 * i] = (uint32_t)t[i]; r.l[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+        r.reduce_once();   // a, b < m < 2^254: the result is below 2m and t[4] is zero
         return r;
 #else
         uint32_t A[9], B[9];

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(128) msm_table_kernel(const uint4* __restrict_
         pref[w] = run;                      // product of t_1..t_{w-1}, t = zz*zzz
         run = run * (cur.zz * cur.zzz);
     }
-    Fq inv = run.inv();
+    Fq inv = fp_inv_bingcd(run);
     for (int w = windows - 1; w >= 1; w--) {
         Fq tinv = inv * pref[w];            // 1/(zz_w * zzz_w)
         inv = inv * (zz[w] * zzz[w]);
@@ -412,7 +412,7 @@ __global__ void g1_normalize_kernel(const uint4* __restrict__ xyz, uint4* __rest
     G1Affine a;
     if (z.is_zero()) { a.x = Fq::zero(); a.y = Fq::zero(); }
     else {
-        Fq zi = z.inv(), zi2 = zi.sqr();
+        Fq zi = fp_inv_bingcd(z), zi2 = zi.sqr();
         a.x = x * zi2;
         a.y = y * (zi2 * zi);
     }
@@ -489,7 +489,7 @@ static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, i
     Fq x = Fq::zero(), y = Fq::one(), z = Fq::zero();
     if (!acc.is_identity()) {
         // x = X/ZZ, y = Y/ZZZ with one inversion of ZZ*ZZZ
-        Fq tinv = (acc.zz * acc.zzz).inv();
+        Fq tinv = fp_inv_bingcd(acc.zz * acc.zzz);
         x = acc.x * (acc.zzz * tinv);
         y = acc.y * (acc.zz * tinv);
         z = Fq::one();

@@ -21,7 +21,6 @@ namespace zkw {
 static const uint64_t kDeltaM[4] = {0x9a0c322befd78855ULL, 0x46e82d14249b563cULL, 0x5983a663e0b0b7a7ULL, 0x22ab452baaa111adULL};
 
 static Fr fr_of(const uint64_t v[4]) { Fr r; memcpy(r.l, v, 32); return r; }
-static Fr fr_small(uint64_t v) { Fr r = Fr::zero(); r.l[0] = (uint32_t)v; r.l[1] = (uint32_t)(v >> 32); return r.to_mont(); }
 
 // ---- transcripts -----------------------------------------------------------------------------------
 struct Transcript {
@@ -280,7 +279,7 @@ static int grand_product(zkw_ctx* ctx, const uint64_t* num, const uint64_t* den,
     Fr total;
     ZKW_CUDA(ctx, cudaMemcpyAsync(total.l, total_dev, 32, cudaMemcpyDeviceToHost, ctx->stream));
     ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const Fr tinv = total.inv();
+    const Fr tinv = fp_inv_bingcd(total);
     { ProfScope ps_(ctx, "grand_product_finalize_kernel"); grand_product_finalize_kernel<<<grid_for(u + 1, 128), 128, 0, ctx->stream>>>((const uint4*)pn, (const uint4*)sd, (const uint4*)z0_dev, tinv, (uint4*)z, u, n); }
     ZKW_LAUNCHED(ctx);
     return rand_fill(ctx, z + 4 * (u + 1), n - (u + 1), seed, stream, 0);
@@ -824,7 +823,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
     ZKW_TRY(sc.get(vb, (void**)&kd_terms));
     ZKW_TRY(sc.get(vb, (void**)&kd_pre));
     auto kate_div = [&](const uint64_t* poly, const Fr& z, uint64_t* q) -> int {
-        const Fr zinv = z.inv();
+        const Fr zinv = fp_inv_bingcd(z);
         { ProfScope ps_(ctx, "kate_terms_kernel"); kate_terms_kernel<<<grid_for((n + 15) / 16, 128), 128, 0, st>>>((const uint4*)poly, (uint4*)kd_terms, z, n); }
         ZKW_LAUNCHED(ctx);
         ZKW_TRY((scan_run<false, false>(ctx, kd_terms, kd_pre, n, blocks, nullptr)));
@@ -884,7 +883,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
                             num.swap(nn);
                             den = den * (rs.pts[i] - rs.pts[j]);
                         }
-                        const Fr cf = vals[k + i] * den.inv();
+                        const Fr cf = vals[k + i] * fp_inv_bingcd(den);
                         for (size_t d = 0; d < num.size(); d++) out[d] = out[d] + cf * num[d];
                     }
                     rs.r_x.push_back(out);
@@ -941,7 +940,7 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
         }
         Fr zt = Fr::one();
         for (auto& d : super_pts) zt = zt * (uch - d);
-        const Fr inv0 = zdiff[0].inv();
+        const Fr inv0 = fp_inv_bingcd(zdiff[0]);
         std::vector<const uint64_t*> ps;
         std::vector<Fr> ws;
         Fr cst = Fr::zero();

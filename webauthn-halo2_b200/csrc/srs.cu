@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(128) fixed_base_kernel(const uint4* __restrict
     G1Affine a;
     if (acc.is_identity()) { a.x = Fq::zero(); a.y = Fq::zero(); }
     else {
-        Fq tinv = (acc.zz * acc.zzz).inv();
+        Fq tinv = fp_inv_bingcd(acc.zz * acc.zzz);
         a.x = acc.x * (acc.zzz * tinv);
         a.y = acc.y * (acc.zz * tinv);
     }
@@ -55,7 +55,7 @@ __global__ void lagrange_scalars_kernel(const uint4* __restrict__ pw, uint4* __r
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr w = Fr::load(pw + 2 * i);
-    Fr d = (tau - w).inv();
+    Fr d = fp_inv_bingcd(tau - w);
     (c * w * d).store(out + 2 * i);
 }
 
@@ -79,7 +79,7 @@ static std::vector<uint64_t> build_fixed_table_host() {
         pref[i] = run;
         if (!pts[i].is_identity()) run = run * (pts[i].zz * pts[i].zzz);
     }
-    Fq inv = run.inv();
+    Fq inv = fp_inv_bingcd(run);
     std::vector<uint64_t> out(pts.size() * 8, 0);
     for (size_t i = pts.size(); i-- > 0;) {
         if (pts[i].is_identity()) continue;
