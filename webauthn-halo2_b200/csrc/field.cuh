@@ -13,6 +13,7 @@
 // integer modular arithmetic.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 namespace zkw {
 
@@ -254,11 +255,9 @@ struct Fp {
         // field arithmetic of the prover, between the device's rounds - it is on the proof's critical path.
         typedef unsigned __int128 u128;
         uint64_t x[4], y[4], md[4];
-        for (int i = 0; i < 4; i++) {
-            x[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
-            y[i] = (uint64_t)b.l[2 * i] | ((uint64_t)b.l[2 * i + 1] << 32);
-            md[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
-        }
+        memcpy(x, a.l, 32);   // eight little-endian u32 limbs are four little-endian u64 limbs (x86-64 host)
+        memcpy(y, b.l, 32);
+        for (int i = 0; i < 4; i++) md[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
         // -m^-1 mod 2^64 from the 32-bit constant: one Newton step on m^-1 mod 2^32
         const uint64_t minv32 = (uint32_t)(0u - P::INV);
         const uint64_t inv64 = 0 - minv32 * (2 - md[0] * minv32);
@@ -273,7 +272,7 @@ struct Fp {
             c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
         }
         Fp r;
-        for (int i = 0; i < 4; i++) { r.l[2 * i] = (uint32_t)t[i]; r.l[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+        memcpy(r.l, t, 32);
         r.reduce_once();   // a, b < m < 2^254: the result is below 2m and t[4] is zero
         return r;
 #else
