@@ -434,6 +434,30 @@ def run_b200(args):
                         "msm_total_ms": sum(v[0] for v in iso.values()) / icnt}
         del us
 
+    # the reference's other flavours through the public API (host witness synthesis + H2D inside, wall clock):
+    # generate_proof = Blake2b + SHPLONK (what bench_secp256r1_ecdsa and the published csv time) at k = 19 and at the
+    # server's k = 17 (BASELINE configs[0]); generate_proof_evm at k = 17 (the /prove_evm production path)
+    flavours = None
+    if args.flavours and args.workload != "hotpath" and rank == 0:
+        flavours = {}
+
+        def time_flavour(st, transcript, shplonk, reps=5):
+            for i in range(2):
+                st.prove(b"flavour-warm-%d" % i, transcript, seed=i, shplonk=shplonk)
+            t0 = time.perf_counter()
+            for i in range(reps):
+                proof = st.prove(b"flavour-%d" % i, transcript, seed=100 + i, shplonk=shplonk)
+            return {"ms_per_proof": (time.perf_counter() - t0) / reps * 1e3, "proof_bytes": len(proof)}
+
+        flavours["k19_blake2b_shplonk"] = time_flavour(state.state, zkw.TRANSCRIPT_BLAKE2B, True)
+        st17 = zkw.ProverState(zkw.CircuitParams.for_degree(17), local)
+        flavours["k17_blake2b_shplonk"] = time_flavour(st17, zkw.TRANSCRIPT_BLAKE2B, True)
+        flavours["k17_evm_gwc"] = time_flavour(st17, zkw.TRANSCRIPT_EVM, False)
+        st17.close()
+        st17.ctx.close()
+        flavours["published_reference_ms"] = {"k19_blake2b_shplonk": 14846.2, "k17_blake2b_shplonk": 5388.0,
+                                               "source": "halo2-circuits/src/results/ecdsa_bench.csv:2,4 (M1 Pro, includes halo2-ecc witness synthesis)"}
+
     # configs[2]-style throughput: a batch of independent proofs through the public API with several
     # provers in flight on this GPU (host witness synthesis included)
     batch = None
@@ -492,7 +516,7 @@ def run_b200(args):
                        "l2": "working set per step ~1.4 GB (14 cosets x 64 MiB + SRS window tables 2 x 512 MiB) exceeds the 126 MB L2"},
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample},
-            "e2e": e2e, "batch": batch, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+            "e2e": e2e, "batch": batch, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
             "published_reference": {"value": 1.0 / 14.846241542, "unit": UNIT, "hardware": "M1 Pro (halo2-circuits/src/results/ecdsa_bench.csv:2)",
                                     "note": "full create_proof incl. halo2-ecc witness synthesis, Blake2b + SHPLONK; not the same hardware or witness"},
         }
@@ -513,6 +537,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="proofs per GPU in the batch-throughput leg: BASELINE configs[2] (64 on one GPU) and [3] (512 over 8); 0 = skip")
     ap.add_argument("--workers", type=int, default=3, help="concurrent provers per GPU in the batch leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-flavours", dest="flavours", action="store_false", help="skip the Blake2b/SHPLONK and k = 17 timings")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
