@@ -6,7 +6,7 @@ names = [r[4].split('(')[0].replace('zkw::', '') for r in rows]
 t = [float(r[14]) / 1e3 for r in rows]   # us
 starts = [i for i, n in enumerate(names) if n in ('to_mont_kernel', 'u64_to_mont_kernel') and i + 1 < len(names) and names[i + 1] in ('zero_fill_kernel', 'rand_fill_kernel')]
 proofs = [(s, e) for s, e in zip(starts, starts[1:] + [len(names)])]
-s, e = proofs[-2]   # a complete timed proof (the last segment also holds bench.py's isolated MSMs)
+s, e = proofs[1]    # the first timed proof (after one warm-up); later segments also hold the isolated MSMs and other flavours
 agg = collections.OrderedDict()
 for n, x in zip(names[s:e], t[s:e]):
     a = agg.setdefault(n, [0, 0.0, 0.0]); a[0] += 1; a[1] += x; a[2] = max(a[2], x)

@@ -1,13 +1,14 @@
-"""Per-launch timeline of one k=19 proof (CUDA events around every kernel, all streams), written as CSV:
+"""Per-launch timeline of one proof (k = 19 by default; second argument = degree) (CUDA events around every kernel, all streams), written as CSV:
 name,stream,start_ms,duration_ms.  Development aid: shows what overlaps what and where the device idles."""
 import importlib, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.getcwd())
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/timeline.csv"
+degree = int(sys.argv[2]) if len(sys.argv) > 2 else 19
 if os.path.exists(out):
     os.remove(out)
 zkw = importlib.import_module("webauthn-halo2_b200")
-st = zkw.ProverState(zkw.CircuitParams.for_degree(19), 0)
+st = zkw.ProverState(zkw.CircuitParams.for_degree(degree), 0)
 ctx = st.ctx
 cols = st.circuit.synthesize(b"a")
 dev = [torch.from_numpy(zkw.circuit.to_limbs(c).view(np.int64)).cuda() for c in cols]
