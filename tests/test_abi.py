@@ -61,3 +61,21 @@ def test_shape_helpers(zkw):
     assert (s.k, s.ext_k, s.cs_degree, s.perm_columns, s.perm_sets, s.lookups) == (17, 19, 4, 6, 3, 1)
     s = zkw.CircuitShape.from_config(11, 291, 53, 4)
     assert (s.ext_k, s.perm_columns, s.perm_sets, s.lookups) == (13, 348, 174, 53)
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, zkw):
+    """gcc -std=c11 compiles a C caller against include/zkw_b200.h and links it with the library alone: what a
+    cgo / Rust `cc` / JNI shim on the reference side would do."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    zkw.load_library()
+    libdir = os.path.join(ROOT, "webauthn-halo2_b200")
+    exe = str(tmp_path / "ffi_caller")
+    cmd = ["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", exe,
+           os.path.join(ROOT, "tests", "host", "ffi_caller.c"), "-L", libdir, "-l:libzkw_b200.so", "-Wl,-rpath," + libdir]
+    subprocess.run(cmd, check=True, capture_output=True)
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "FFI_CALLER OK" in res.stdout
