@@ -115,6 +115,36 @@ struct G1Xyzz {
         zzz = zzz * ppp;
     }
 
+    // this += b (affine, canonical coordinates) with the running point's coordinates lazily reduced (in [0, 2p),
+    // see field.cuh): same formulas as add_mixed, ten products without their final conditional subtraction.
+    // The result is again in [0, 2p); call normalize() before the point leaves the kernel.
+    __device__ __forceinline__ void add_mixed_lazy(const G1Affine& b_in, bool negate) {
+        if (b_in.is_identity()) return;
+        G1Affine b = b_in;
+        if (negate) b.y = b.y.neg();
+        if (is_identity()) { *this = from_affine(b); return; }
+        Fq u2 = Fq::mul_lazy(b.x, zz);
+        Fq s2 = Fq::mul_lazy(b.y, zzz);
+        Fq p = Fq::sub_lazy(u2, x);
+        Fq r = Fq::sub_lazy(s2, y);
+        if (p.is_zero_lazy()) {   // same x: doubling or cancellation, through the canonical formulas
+            normalize();
+            add_mixed(b, false);
+            return;
+        }
+        Fq pp = Fq::mul_lazy(p, p);
+        Fq ppp = Fq::mul_lazy(p, pp);
+        Fq q = Fq::mul_lazy(x, pp);
+        Fq x3 = Fq::sub_lazy(Fq::sub_lazy(Fq::mul_lazy(r, r), ppp), Fq::add_lazy(q, q));
+        y = Fq::sub_lazy(Fq::mul_lazy(r, Fq::sub_lazy(q, x3)), Fq::mul_lazy(y, ppp));
+        x = x3;
+        zz = Fq::mul_lazy(zz, pp);
+        zzz = Fq::mul_lazy(zzz, ppp);
+    }
+    __host__ __device__ __forceinline__ void normalize() {
+        x = x.normalized(); y = y.normalized(); zz = zz.normalized(); zzz = zzz.normalized();
+    }
+
     // this += b (XYZZ)
     __host__ __device__ __forceinline__ void add(const G1Xyzz& b) {
         if (b.is_identity()) return;

@@ -207,13 +207,19 @@ msm_accumulate_kernel(const uint4* __restrict__ points, const uint32_t* __restri
             nxt = G1Affine::load_nc(points + 4 * (size_t)(e & 0x7fffffffu));
         }
         if (k == bend) {   // entry k opens the next non-empty bucket: emit the finished one
+            acc.normalize();
             acc.store(partials + 8 * ((size_t)t + b));
             acc = G1Xyzz::identity();
             do { b++; bend = offsets[b + 1]; } while (bend <= k);
         }
+#ifdef ZKW_MSM_NO_LAZY
         acc.add_mixed(cur, neg);
+#else
+        acc.add_mixed_lazy(cur, neg);   // running point kept in [0, 2p): no conditional subtraction after the products
+#endif
         cur = nxt;
     }
+    acc.normalize();
     acc.store(partials + 8 * ((size_t)t + b));
 }
 
