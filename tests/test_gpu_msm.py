@@ -177,3 +177,51 @@ def test_msm_full_size_split_identity_k19(zkw, oracle):
         assert np.array_equal(_affine(oracle, s), whole[:8])
     finally:
         c.close()
+
+
+def _witness_like_columns(oracle, n, lookup_bits=18):
+    """Scalar vectors shaped like the columns a k = 19 proof commits to: an advice column (bits, lookup limbs,
+    88-bit limbs, a few full-width values), the sorted permuted lookup column A', and a grand-product column Z
+    (full-width values with long constant stretches)."""
+    from oracle import pyref as pr
+    rng = np.random.default_rng(1919)
+    kind = rng.integers(0, 8, n)
+    small = rng.integers(0, 1 << lookup_bits, n, dtype=np.uint64)
+    wide = oracle.fr_from_mont(oracle.fr_random(n // 8 + 1, 7))
+    adv = []
+    for i in range(n):
+        t = int(kind[i])
+        if t < 2:
+            adv.append(int(small[i]) & 1)
+        elif t < 5:
+            adv.append(int(small[i]))
+        elif t < 7:
+            adv.append((int(small[i]) << 70) | int(small[(i + 1) % n]) << 20 | 5)    # 88-bit limb
+        else:
+            adv.append(wide[i // 8])
+    a_prime = sorted(int(x) for x in small)
+    z = []
+    cur = wide[0]
+    for i in range(n):
+        if int(kind[i]) == 0 and i % 97 == 0:
+            cur = wide[(i // 8) % len(wide)]
+        z.append(cur if i % 5 else (cur * (i + 1)) % pr.R)
+    return {"advice": adv, "a_prime": a_prime, "z": z}
+
+
+def test_msm_full_size_k19_matches_oracle_bit_for_bit(zkw, oracle):
+    """BASELINE size: ONE 2^19-point MSM over the resident window-table path (c = 16, 592-CTA run plan, heavy
+    bucket queue) compared bit for bit with the oracle's best_multiexp — uniform scalars and the three
+    witness-shaped columns a k = 19 proof commits to."""
+    n = 1 << 19
+    c = zkw.Context(0)
+    try:
+        g = _bases(oracle, n, 61)
+        c.srs_load(g, None)
+        s = oracle.fr_random(n, 62)
+        assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s, g)))
+        for name, vals in _witness_like_columns(oracle, n).items():
+            s = oracle.fr_to_mont(vals)
+            assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s, g))), name
+    finally:
+        c.close()

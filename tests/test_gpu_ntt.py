@@ -118,3 +118,34 @@ def test_full_size_round_trip_k19(ctx, oracle):
     for i in (0, 1, 12345, (1 << ek) - 1):
         x = dom.g_coset * pow(dom.extended_omega, i, pr.R) % pr.R
         assert oracle.fr_from_mont(ext[i:i + 1])[0] == pr.poly_eval(cv, x)
+
+
+def test_full_size_transforms_k19_match_oracle_bit_for_bit(ctx, oracle):
+    """BASELINE size, every element compared with the oracle: lagrange_to_coeff at 2^19, coeff_to_extended
+    2^19 -> 2^21, extended_to_coeff at 2^21 (on an arbitrary vector, not only on an image of the extension),
+    and a plain best_fft at 2^21."""
+    k, ek = 19, 21
+    d = oracle.Domain.new(5, k)
+    assert d.ext_k == ek
+    a = oracle.fr_random(1 << k, 777)
+    coeff = ctx.lagrange_to_coeff(a)
+    assert np.array_equal(coeff, d.lagrange_to_coeff(a))
+    ext = ctx.coeff_to_extended(coeff, ek)
+    assert np.array_equal(ext, d.coeff_to_extended(coeff))
+    e = oracle.fr_random(1 << ek, 778)
+    assert np.array_equal(ctx.extended_to_coeff(e), d.extended_to_coeff(e))
+    _, om = _omega(oracle, ek)
+    assert np.array_equal(ctx.ntt(e, om), oracle.best_fft(e, om))
+
+
+def test_full_size_transforms_k17_match_oracle_bit_for_bit(ctx, oracle):
+    """The server's degree (proving-server/src/main.rs:17): 2^17 rows, extended 2^19 (constraint degree 4)."""
+    k = 17
+    d = oracle.Domain.new(4, k)
+    a = oracle.fr_random(1 << k, 779)
+    coeff = ctx.lagrange_to_coeff(a)
+    assert np.array_equal(coeff, d.lagrange_to_coeff(a))
+    ext = ctx.coeff_to_extended(coeff, d.ext_k)
+    assert np.array_equal(ext, d.coeff_to_extended(coeff))
+    e = oracle.fr_random(1 << d.ext_k, 780)
+    assert np.array_equal(ctx.extended_to_coeff(e), d.extended_to_coeff(e))

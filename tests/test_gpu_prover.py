@@ -10,6 +10,8 @@ permutation, witness and blinding stream:
     acceptance only (oracle verifier, known-tau form of the pairing check), plus rejection of a
     corrupted witness.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -209,3 +211,62 @@ def test_prover_abi_error_paths(zkw, oracle):
         pk.close()
     finally:
         ctx.close()
+
+
+# ---- N1: the reference's own verifier judges device proofs (no known-tau shortcut) ----------------------
+YUL = "/root/reference/proving-server/P256Verifier.yul"
+GX = bytes.fromhex("6b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296")[::-1]
+GY = bytes.fromhex("4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5")[::-1]
+
+
+def _k17_evm_device_proof(zkw, oracle):
+    import hashlib
+    from oracle import halo2_ref as h
+    from tests.assertions import signed_assertion
+    a = signed_assertion(17)
+    proof = zkw.generate_proof_evm(a["pubkey_x"], a["pubkey_y"], a["r"], a["s"], a["msg_hash"], "./keys/proving_key.pk", 17, seed=5)
+    st = zkw.download_keys(17, "./keys/proving_key.pk")
+    vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(17, 4, 1, 1))
+    return proof, vk
+
+
+def test_k17_evm_device_proof_accepted_with_real_pairing(zkw, oracle):
+    """The k = 17 EVM/GWC device proof (the server's flavour, proving-server/src/main.rs:17,49-63) goes through
+    halo2_ref.verify_proof with the REAL pairing e(left, s*G2) == e(right, G2) (own BN254 pairing, the one that
+    accepts the reference's golden proof) — no known-tau shortcut; tampered proofs are rejected."""
+    import json
+    import os
+    from oracle import halo2_ref as h, pairing as pg
+    proof, vk = _k17_evm_device_proof(zkw, oracle)
+    tau = zkw.prover.DEV_TAU_CANONICAL
+    g2_pair = (pg.G2_GEN, pg.g2_mul(pg.G2_GEN, tau))
+    assert len(proof) == 2720
+    assert h.verify_proof(vk, proof, "evm", g2_pair=g2_pair)
+    for pos in (3, 1000, 2719):
+        bad = bytearray(proof)
+        bad[pos] ^= 1
+        assert not h.verify_proof(vk, bytes(bad), "evm", g2_pair=g2_pair)
+    # leave the proof + key for tools/make_device_proof_fixture.py (tests/golden/device_proof_k17_evm.json): the
+    # CPU suite runs that fixture through the reference's Yul verifier where /root/reference is mounted
+    out = {"proof": proof.hex(), "digest": str(vk.digest), "fixed": [[hex(x), hex(y)] for x, y in vk.fixed_commitments],
+           "perm": [[hex(x), hex(y)] for x, y in vk.perm_commitments], "tau": hex(tau), "seed": 5}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/device_proof_k17_evm.json", "w") as f:
+        json.dump(out, f)
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "device_proof_k17_evm.json")
+    if os.path.exists(fixture):
+        want = json.load(open(fixture))
+        assert want["proof"] == out["proof"] and want["digest"] == out["digest"], "device proof differs from the committed fixture"
+
+
+@pytest.mark.skipif(not os.path.exists(YUL), reason="reference not mounted on this box (the Yul is never copied into the repo); "
+                    "the CPU suite runs the committed device-proof fixture through it instead (tests/test_device_proof_fixture.py)")
+def test_k17_evm_device_proof_accepted_by_reference_yul(zkw, oracle):
+    from oracle import yul_evm, yul_patch
+    proof, vk = _k17_evm_device_proof(zkw, oracle)
+    src = yul_patch.patch_verifier(open(YUL).read(), vk.digest, vk.g0, vk.fixed_commitments, vk.perm_commitments, zkw.prover.DEV_TAU_CANONICAL)
+    ok, m = yul_evm.run_verifier(src, proof)
+    assert ok and m.precompile_calls[8] == 1
+    bad = bytearray(proof)
+    bad[77] ^= 1
+    assert not yul_evm.run_verifier(src, bytes(bad))[0]

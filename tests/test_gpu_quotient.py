@@ -65,3 +65,15 @@ def test_quotient_rejects_bad_shapes(ctx, zkw, oracle):
     sel = zkw.CircuitShape(4, 6, 2, 0, 1, 6, 5, 0)  # selector mode needs exactly one gate column
     with pytest.raises(zkw.ZkwError):
         ctx.quotient(sel, cols, ch)
+
+
+@pytest.mark.parametrize("k,A,L,F", [(19, 1, 0, 1), (17, 4, 1, 1)])
+def test_quotient_full_size_matches_oracle_bit_for_bit(ctx, zkw, oracle, k, A, L, F):
+    """BASELINE sizes: k = 19 (bench_ecdsa.config:1; 2^21 extended rows, 14 input cosets) and k = 17
+    (ecdsa_circuit.config:1; 2^19 extended rows), every row compared with the oracle's evaluate_h restatement."""
+    oshape = oracle.make_shape(k, A, L, F)
+    shape = zkw.CircuitShape(*[getattr(oshape, f) for f, _ in oshape._fields_])
+    cols, ch = random_inputs(oracle, oshape, k)
+    want = oracle.quotient_ecdsa(oshape, cols, ch)
+    got = ctx.quotient(shape, cols, ch)
+    assert np.array_equal(got, want)
