@@ -48,7 +48,7 @@ WORKLOAD_HOT = ("ECDSA circuit k=19 (1 advice/1 lookup/1 fixed, ext 2^21), prove
                 "15 MSM(2^19) + 5 iNTT(2^19) + 5 cosetNTT(2^19->2^21) + quotient(2^21 rows) + 1 iNTT(2^21), GWC opening count")
 WORKLOAD = ("single P-256 ECDSA-circuit proof, k=19 (bench_ecdsa.config:1: 1 advice/1 lookup/1 fixed, ext 2^21), EVM transcript, GWC: "
             "full create_proof on the device (15 MSM(2^19), 5 iNTT, 5 coset NTT, quotient, lookup permutation, grand products, "
-            "18 evaluations, 5 openings) on a shape-identical synthetic witness")
+            "18 evaluations, 5 openings) on the P-256 ECDSA verification circuit's witness for a synthetic signed WebAuthn assertion")
 
 
 def peaks():
@@ -57,6 +57,56 @@ def peaks():
         with open(p) as f:
             return json.load(f), "measured"
     return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def ncu_dram_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, read from the newest committed
+    `ncu --set full --page raw --csv` export under profiles/ (per-launch, like `achieved`); (None, why) if absent."""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_msm_acc*_raw.csv")), reverse=True):
+        try:
+            with open(path, newline="") as f:
+                rows = list(csv.reader(f))
+        except OSError:
+            continue
+        hdr = next((r for r in rows if "Kernel Name" in r), None)
+        if not hdr:
+            continue
+        ik = hdr.index("Kernel Name")
+        try:
+            ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        except ValueError:
+            continue
+        units = rows[rows.index(hdr) + 1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = []
+        for r in rows[rows.index(hdr) + 2:]:
+            if len(r) > max(ik, ir, iw) and kernel in r[ik]:
+                try:
+                    vals.append(float(r[ir].replace(",", "")) * scale.get(units[ir], 1.0) + float(r[iw].replace(",", "")) * scale.get(units[iw], 1.0))
+                except ValueError:
+                    pass
+        if vals:
+            best = (sum(vals) / len(vals), f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, mean of {len(vals)} launch(es) in {os.path.relpath(path, ROOT)}")
+            break
+    return best or (None, "no ncu raw export of this kernel under profiles/")
+
+
+def modmul_peak_from_profiles():
+    """Measured 254-bit Montgomery products per second of one B200 (tools/modmul_bench.cu), from the newest profiles/r*_modmul_peak.txt."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_modmul_peak.txt")), reverse=True):
+        try:
+            vals = [float(x) for x in re.findall(r"([0-9.]+)\s*G\s*(?:products|modmul)", open(path).read())]
+            m = max(vals) if vals else None
+        except OSError:
+            continue
+        if m:
+            return m * 1e9, os.path.relpath(path, ROOT)
+    return None, "no profiles/r*_modmul_peak.txt"
 
 
 class ClockSampler:
@@ -225,19 +275,22 @@ class HostAbiProof:
 
 
 class FullProof:
-    """One complete create_proof per step through zkw_create_proof_ex (EVM transcript, GWC)."""
+    """One complete create_proof per step through zkw_create_proof_ex (EVM transcript, GWC) over the real P-256
+    ECDSA verification circuit (csrc/ecdsa_circuit.cpp) for synthetic signed WebAuthn assertions."""
 
     def __init__(self, zkw, torch, k: int, device: int, seed: int):
         self.zkw, self.torch = zkw, torch
         self.state = zkw.ProverState(zkw.CircuitParams.for_degree(k), device)      # gen_srs + keygen, resident
         self.ctx = self.state.ctx
-        self.assertions = [b"synthetic-webauthn-assertion-%d-%d" % (seed, i) for i in range(4)]
-        cols = [self.zkw.circuit.to_limbs(c) for c in self.state.circuit.synthesize(self.assertions[0])]
+        self.assertions = [zkw.synthetic_assertion(1000 * seed + i) for i in range(4)]
+        a = self.assertions[0]
+        cols = self.state.circuit.synthesize(*[a[32 * i: 32 * i + 32] for i in range(5)])     # canonical integers
         self.rows = [c.shape[0] for c in cols]
         self.dev_cols = [torch.from_numpy(c.view(np.int64)).to(torch.device("cuda", device)) for c in cols]
         self.step_no = 0
         self.proof = b""
-        self.h2d = sum(c.shape[0] * 8 for c in cols)      # the public API ships one u64 per advice row
+        self.h2d = sum(c.shape[0] * 32 for c in cols)      # the public API ships the assigned advice cells, 32 bytes each
+        self.synth_ms = []
 
     def step(self):
         """advice already in HBM (canonical integers); blinding seed changes every step."""
@@ -250,33 +303,69 @@ class FullProof:
         """the public API: assertion bytes in, proof bytes out (host witness synthesis + H2D inside)."""
         self.step_no += 1
         self.proof = self.state.prove(self.assertions[self.step_no % len(self.assertions)], self.zkw.TRANSCRIPT_EVM, seed=self.step_no)
+        self.synth_ms.append(self.state.last_synth_ms)
         return self.proof
 
 
-def cpu_hot_path(k: int, threads: int):
-    """Times one of each hot-path call on the CPU oracle and scales by the per-proof counts.
-    Returns (proofs_per_s, sample description, per-call seconds)."""
-    from oracle import cpu
-    n = 1 << k
-    shape = cpu.make_shape(k, 1, 0, 1)
-    ek, en = shape.ext_k, 1 << shape.ext_k
-    dom = cpu.Domain.new(shape.cs_degree, k)
-    t = {}
-    bases = cpu.g1_fixed_base_mul(cpu.fr_random(n, 1), threads)
-    s = cpu.fr_random(n, 2)
-    t0 = time.perf_counter(); cpu.best_multiexp(s, bases, threads); t["msm"] = time.perf_counter() - t0
-    a = cpu.fr_random(n, 3)
-    t0 = time.perf_counter(); c = dom.lagrange_to_coeff(a, threads); t["intt"] = time.perf_counter() - t0
-    t0 = time.perf_counter(); e = dom.coeff_to_extended(c, threads); t["ext"] = time.perf_counter() - t0
-    t0 = time.perf_counter(); dom.extended_to_coeff(e, threads); t["iext"] = time.perf_counter() - t0
-    cols = {"advice": [e], "constants": [e], "table": e, "q_enable": [e], "q_lookup": e, "sigma": [e, e],
-            "perm_z": [e], "lookup_z": [e], "lookup_a": [e], "lookup_s": [e], "l0": e, "l_last": e, "l_active": e}
-    ch = {nme: cpu.fr_random(1, 9)[0] for nme in ("y", "beta", "gamma", "theta")}
-    t0 = time.perf_counter(); cpu.quotient_ecdsa(shape, cols, ch, threads); t["quot"] = time.perf_counter() - t0
-    per_proof = (N_MSM_G + N_MSM_LAGRANGE) * t["msm"] + N_INTT * t["intt"] + N_EXT * t["ext"] + N_IEXT * t["iext"] + N_QUOT * t["quot"]
-    sample = (f"one call each of best_multiexp(2^{k}), lagrange_to_coeff(2^{k}), coeff_to_extended(2^{k}->2^{ek}), "
-              f"extended_to_coeff(2^{ek}), evaluate_h(2^{ek} rows) on {threads} threads, scaled by the per-proof counts 15/5/5/1/1")
-    return 1.0 / per_proof, sample, t
+class CpuHotPath:
+    """The reference arm / cpu_baseline leg: the prover's hot-path call sequence for ONE k = 19 proof on the CPU oracle
+    (a restatement of the upstream CPU algorithms), every call on its own buffers:
+
+        15 best_multiexp(2^k) on 15 distinct scalar vectors (5 over g_lagrange, 10 over g)
+         5 lagrange_to_coeff(2^k), 5 coeff_to_extended(2^k -> 2^ek) on 5 distinct columns
+         1 evaluate_h + divide_by_vanishing_poly over 14 distinct cosets, 1 extended_to_coeff(2^ek)
+
+    `fraction` < 1 runs a bounded sample: ceil(fraction * count) calls of each kind (the quotient over the first
+    fraction of the rows is not expressible, so it is run whole and its measured time is scaled); the value reported is
+    always proofs per second = fraction_of_a_proof_done / measured_seconds, and ms_per_step is the measured time."""
+
+    def __init__(self, k: int, threads: int):
+        from oracle import cpu
+        self.cpu, self.k, self.threads = cpu, k, threads
+        n = 1 << k
+        self.shape = cpu.make_shape(k, 1, 0, 1)
+        self.ek = self.shape.ext_k
+        en = 1 << self.ek
+        self.dom = cpu.Domain.new(self.shape.cs_degree, k)
+        self.g = cpu.g1_fixed_base_mul(cpu.fr_random(n, 1), threads)
+        self.gl = cpu.g1_fixed_base_mul(cpu.fr_random(n, 2), threads)
+        self.scalars = [cpu.fr_random(n, 10 + i) for i in range(N_MSM_G + N_MSM_LAGRANGE)]
+        self.columns = [cpu.fr_random(n, 40 + i) for i in range(N_INTT)]
+        names = ("constants", "table", "q_enable", "q_lookup", "sigma0", "sigma1", "l0", "l_last", "l_active")
+        self.pk = {nm: cpu.fr_random(en, 60 + i) for i, nm in enumerate(names)}
+        self.ch = {nme: cpu.fr_random(1, 90 + i)[0] for i, nme in enumerate(("y", "beta", "gamma", "theta"))}
+
+    def step(self) -> dict:
+        cpu, dom, T = self.cpu, self.dom, self.threads
+        t = {}
+        t0 = time.perf_counter()
+        for i, s in enumerate(self.scalars):
+            cpu.best_multiexp(s, self.gl if i < N_MSM_LAGRANGE else self.g, T)
+        t["msm"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        coeffs = [dom.lagrange_to_coeff(c, T) for c in self.columns]
+        t["intt"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        ext = [dom.coeff_to_extended(c, T) for c in coeffs]
+        t["ext"] = time.perf_counter() - t0
+        pk = self.pk
+        cols = {"advice": [ext[0]], "constants": [pk["constants"]], "table": pk["table"], "q_enable": [pk["q_enable"]],
+                "q_lookup": pk["q_lookup"], "sigma": [pk["sigma0"], pk["sigma1"]], "perm_z": [ext[3]], "lookup_z": [ext[4]],
+                "lookup_a": [ext[1]], "lookup_s": [ext[2]], "l0": pk["l0"], "l_last": pk["l_last"], "l_active": pk["l_active"]}
+        t0 = time.perf_counter()
+        h = cpu.quotient_ecdsa(self.shape, cols, self.ch, T)
+        t["quot"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        dom.extended_to_coeff(h, T)
+        t["iext"] = time.perf_counter() - t0
+        t["total"] = sum(t.values())
+        return t
+
+    def sample(self) -> str:
+        return (f"the whole hot-path sequence of one proof, each call on its own buffers: {N_MSM_G + N_MSM_LAGRANGE} best_multiexp(2^{self.k}), "
+                f"{N_INTT} lagrange_to_coeff(2^{self.k}), {N_EXT} coeff_to_extended(2^{self.k}->2^{self.ek}), evaluate_h(2^{self.ek} rows, 14 cosets), "
+                f"extended_to_coeff(2^{self.ek}); {self.threads} OpenMP threads; not included: witness synthesis, lookup permutation, grand products, "
+                f"evaluations, openings, transcript (the GPU arm does all of those)")
 
 
 def host_threads() -> int:
@@ -288,31 +377,36 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def config_dict(args, workload: str) -> dict:
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workload, "k": args.k, "proofs_per_step_per_gpu": 1,
+            "l2": "working set per step ~1.4 GB (14 cosets x 64 MiB + SRS window tables 2 x 512 MiB) exceeds the 126 MB L2"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
-        return
+        return                                    # N > 1: rank 0 alone runs the CPU arm, the other ranks exit without work
     threads = host_threads()
-    vals = []
-    sample = ""
+    cpu = CpuHotPath(args.k, threads)
+    times = []
     for i in range(args.warmup + args.steps):
-        v, sample, _ = cpu_hot_path(args.k, threads)
+        t = cpu.step()
         if i >= args.warmup:
-            vals.append(v)
-        if i == 0 and args.warmup + args.steps > 2:
-            pass
-    # harmonic mean == total proofs / total time
-    value = len(vals) / sum(1.0 / v for v in vals)
+            times.append(t)
+    total = sum(t["total"] for t in times)
+    value = len(times) / total                    # one step = the hot path of one whole proof, actually run
+    parts = {nm: sum(t[nm] for t in times) / len(times) for nm in ("msm", "intt", "ext", "quot", "iext")}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64x4 Montgomery (254-bit modular integers)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "k": args.k,
-                   "note": "CPU arm times the five hot-path functions only (MSM/NTT/quotient), not the glue between them"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 Montgomery (254-bit modular integers)", "data": "synthetic",
+        "config": config_dict(args, WORKLOAD),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": cpu.sample()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "CPU restatement of the upstream algorithms (oracle/); the Rust prover cannot be built in this image",
+        "gpu_launches": 0, "seconds_per_step_by_function": parts,
+        "note": ("CPU restatement of the upstream algorithms (oracle/, kind \"port\"): the Rust prover cannot be built in this image. It runs "
+                 "LESS work per step than the GPU arm (hot-path functions only, uniformly random columns)"),
     }
     print(json.dumps(line), flush=True)
 
@@ -389,8 +483,26 @@ def run_b200(args):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * e2e_steps / float(te.item()), "unit": UNIT, "h2d_bytes_per_step": state.h2d,
                "d2h_bytes_per_step": len(state.proof), "steps": e2e_steps,
-               "path": "generate_proof_evm mirror (ProverState.prove): assertion bytes -> host witness synthesis (zkw_synth_witness into "
-                       "page-locked staging) -> one H2D copy of the advice column -> zkw_create_proof_ex -> proof bytes"}
+               "host_synthesis_ms": (sum(state.synth_ms) / len(state.synth_ms)) if state.synth_ms else None,
+               "path": "generate_proof_evm mirror (ProverState.prove): assertion bytes -> ECDSA circuit witness synthesis on the host "
+                       "(zkw_ecdsa_synthesize into page-locked staging, signature checked) -> one H2D copy of the assigned advice cells -> "
+                       "zkw_create_proof_ex -> proof bytes"}
+        # the function-level drop-in (what a [patch]ed halo2_proofs pays): the same hot-path sequence through the three
+        # host-pointer seams, host<->device copies of every call inside the timed region
+        if rank == 0 and args.three_seam:
+            hctx = zkw.Context(local)
+            hs = HotPathProof(zkw, hctx, torch, args.k, seed=77)
+            host = HostAbiProof(zkw, hctx, torch, hs)
+            host.step()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                host.step()
+            hctx.sync()
+            e2e["three_seam"] = {"value": 2 / (time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
+                                 "path": "host-pointer C ABI, one call per upstream function (15 zkw_msm_bn254_g1, 5 zkw_lagrange_to_coeff, "
+                                         "5 zkw_coeff_to_extended, zkw_quotient_ecdsa, zkw_extended_to_coeff), caller buffers in host memory"}
+            del host, hs
+            hctx.close()
     elif not args.no_e2e:
         host = HostAbiProof(zkw, ctx, torch, state)
         host.step()
@@ -443,10 +555,10 @@ def run_b200(args):
 
         def time_flavour(st, transcript, shplonk, reps=5):
             for i in range(2):
-                st.prove(b"flavour-warm-%d" % i, transcript, seed=i, shplonk=shplonk)
+                st.prove(state.assertions[i % 4], transcript, seed=i, shplonk=shplonk)
             t0 = time.perf_counter()
             for i in range(reps):
-                proof = st.prove(b"flavour-%d" % i, transcript, seed=100 + i, shplonk=shplonk)
+                proof = st.prove(state.assertions[i % 4], transcript, seed=100 + i, shplonk=shplonk)
             return {"ms_per_proof": (time.perf_counter() - t0) / reps * 1e3, "proof_bytes": len(proof)}
 
         flavours["k19_blake2b_shplonk"] = time_flavour(state.state, zkw.TRANSCRIPT_BLAKE2B, True)
@@ -463,18 +575,18 @@ def run_b200(args):
     batch = None
     if args.batch > 0 and args.workload != "hotpath":
         pool = zkw.ProverPool(zkw.CircuitParams.for_degree(args.k), local, workers=args.workers)
-        assertions = [b"synthetic-webauthn-assertion-%d-%d" % (rank, i) for i in range(args.batch)]
+        assertions = [zkw.synthetic_assertion(100000 * (rank + 1) + i) for i in range(args.batch)]
         pool.prove_many(assertions[: args.workers], zkw.TRANSCRIPT_EVM)          # warm-up (arenas, lanes)
         barrier()
         t0 = time.perf_counter()
-        proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM, seed0=1000)
+        proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         tb_ = torch.tensor([wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tb_, op=dist.ReduceOp.MAX)
         batch = {"proofs_per_gpu": args.batch, "workers_per_gpu": args.workers, "value": world * args.batch / float(tb_.item()), "unit": UNIT,
-                 "path": "ProverPool.prove_many (generate_proof_evm mirror, host witness synthesis + H2D inside)",
+                 "path": "ProverPool.prove_many (generate_proof_evm mirror: ECDSA witness synthesis on the host + H2D inside, OS-seeded blinding)",
                  "all_proofs_distinct": len(set(proofs)) == len(proofs)}
         pool.close()
 
@@ -486,10 +598,12 @@ def run_b200(args):
         alg_bytes = 96 * n
         achieved = (alg_bytes / (per_launch_ms / 1000.0) / 1e9) if per_launch_ms else None
         total_kernel_ms = sum(v[0] for v in prof.values())
+        traffic, traffic_src = ncu_dram_traffic("msm_accumulate_kernel")
+        modmul_peak, modmul_src = modmul_peak_from_profiles()
         roofline = {
             "kernel": "msm_accumulate_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": (achieved / pk["hbm_gbs"]) if achieved else None,
-            "traffic": 1.0575e9, "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one uniform-scalar launch (profiles/r1c_prof_msm_acc_raw.csv, summary in profiles/r1c_ncu_summary.md)",
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": pk_src + " copy bandwidth (MEASURED_PEAKS.json)",
             "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_launch_ms, "launches": acc_cnt,
             "share_of_kernel_time": (acc_ms / total_kernel_ms) if total_kernel_ms else None,
@@ -499,21 +613,25 @@ def run_b200(args):
             "isolated": isolated,
             "isolated_achieved_gbs": (alg_bytes / (isolated["avg_launch_ms"] / 1000.0) / 1e9) if isolated else None,
             "isolated_modmul_per_s": (16 * n * 10 / (isolated["avg_launch_ms"] / 1000.0)) if isolated else None,
-            "modmul_peak_per_s_measured": 68.5e9,
+            "modmul_peak_per_s_measured": modmul_peak, "modmul_peak_source": modmul_src,
         }
         kernels = {name: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for name, v in sorted(prof.items())}
-        cpu_val, cpu_sample, _ = (None, "skipped", None)
+        cpu_val, cpu_sample = None, "skipped"
         cores = None
         if world == 1 and not args.no_cpu:
             cores = host_threads()
-            cpu_val, cpu_sample, _ = cpu_hot_path(args.k, cores)
+            cpu = CpuHotPath(args.k, cores)
+            cpu.step()                                         # warm-up (page faults, OpenMP pool)
+            reps = [cpu.step()["total"] for _ in range(2)]     # ~2 x 7 s on 16 cores: a bounded sample of the reference arm's step
+            cpu_val, cpu_sample = len(reps) / sum(reps), cpu.sample() + f"; {len(reps)} timed steps after one warm-up"
+            del cpu
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32x8 Montgomery (254-bit modular integers)", "data": "synthetic",
-            "config": {"workload": WORKLOAD if args.workload != "hotpath" else WORKLOAD_HOT, "k": args.k, "proofs_per_step_per_gpu": 1,
-                       "proof_bytes": len(getattr(state, "proof", b"")),
-                       "l2": "working set per step ~1.4 GB (14 cosets x 64 MiB + SRS window tables 2 x 512 MiB) exceeds the 126 MB L2"},
+            "config": config_dict(args, WORKLOAD if args.workload != "hotpath" else WORKLOAD_HOT),
+            "proof_bytes": len(getattr(state, "proof", b"")),
+            "circuit": state.state.circuit.stats() if args.workload != "hotpath" else None,
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample},
             "e2e": e2e, "batch": batch, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
@@ -539,6 +657,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flavours", dest="flavours", action="store_false", help="skip the Blake2b/SHPLONK and k = 17 timings")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-three-seam", dest="three_seam", action="store_false", help="skip the host-pointer three-seam figure")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
     # first collective), so file descriptor 1 is pointed at stderr for the whole run and the JSON line alone goes

@@ -241,6 +241,35 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
 int zkw_synth_witness(const zkw_circuit_shape* shape, uint32_t lookup_bits, const uint8_t* assertion, size_t assertion_len,
                       uint64_t* const* cols_out, size_t* rows_out);
 
+/* ---- the P-256 ECDSA verification circuit: ECDSACircuit::{configure, synthesize} (ecdsa_p256.rs:94-206) --------
+ * The one-line JSON config of the reference (struct CircuitParams, ecdsa_p256.rs:53-63; strategy is always "Simple"). */
+typedef struct {
+    uint32_t degree, num_advice, num_lookup_advice, num_fixed, lookup_bits, limb_bits, num_limbs;
+} zkw_circuit_params;
+typedef struct zkw_ecdsa_circuit zkw_ecdsa_circuit;
+
+/* Lays out the circuit once (keygen's `without_witnesses` pass): selectors, copy constraints, constants, lookup
+ * cells.  ZKW_ERR_UNSUPPORTED if it does not fit the 2^degree - 7 usable rows of the given columns (the handle is
+ * still returned for zkw_ecdsa_circuit_rows).  Pure host code: no device, no context. */
+int zkw_ecdsa_circuit_new(const zkw_circuit_params* params, zkw_ecdsa_circuit** out);
+void zkw_ecdsa_circuit_free(zkw_ecdsa_circuit* c);
+int zkw_ecdsa_circuit_shape(const zkw_ecdsa_circuit* c, zkw_circuit_shape* out);
+/* rows_out[num_advice + lookup columns]: cells assigned per advice column; stats_out (may be NULL): gate cells,
+ * lookup cells, distinct constants, copy constraints. */
+int zkw_ecdsa_circuit_rows(const zkw_ecdsa_circuit* c, size_t* rows_out, uint64_t stats_out[4]);
+/* keygen inputs, in the layout zkw_keygen takes: fixed_out[num_fixed + 1 + num_advice (+1)] arrays of 2^degree * 4
+ * u64 CANONICAL integers (convert with zkw_fr_to_mont); mapping_out[num_fixed + num_advice + lookup columns] arrays
+ * of 2^degree (col', row') u32 pairs — every copy class closed into a cycle in increasing (col, row) order. */
+int zkw_ecdsa_circuit_fixed(const zkw_ecdsa_circuit* c, uint64_t* const* fixed_out);
+int zkw_ecdsa_circuit_permutation(const zkw_ecdsa_circuit* c, uint32_t* const* mapping_out);
+/* Witness synthesis for one assertion: the five 32-byte little-endian canonical encodings generate_proof{,_evm}
+ * take (ecdsa_p256.rs:329,379).  advice_out[c]: rows(c) * 4 u64 CANONICAL integers (zkw_ecdsa_circuit_rows gives the
+ * sizes; pass the arrays to zkw_create_proof_ex with ZKW_ADVICE_CANONICAL).  *signature_ok (may be NULL) = 1 iff
+ * the assignment satisfies the circuit, i.e. the signature verifies; the cells are written either way. */
+int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pubkey_x[32], const uint8_t pubkey_y[32], const uint8_t r[32],
+                         const uint8_t s[32], const uint8_t msg_hash[32], uint64_t* const* advice_out, size_t* rows_out,
+                         int* signature_ok);
+
 /* Fr vectors between canonical little-endian integers (< 2r accepted) and halo2curves' Montgomery form;
  * host pointers, n elements of 4 u64. */
 int zkw_fr_to_mont(zkw_ctx* ctx, const uint64_t* canonical, uint64_t* out, size_t n);

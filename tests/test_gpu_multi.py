@@ -43,7 +43,7 @@ def _worker(rank, world, port, n, q):
     want = cpu.g1_to_affine(cpu.best_multiexp(s, b, 2))[0]
     ok_msm = bool(np.array_equal(out[:8], want))
     # independent proofs, sharded round-robin: each rank proves its share on its own GPU
-    st = zkw.ProverState(zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3), rank)
+    st = zkw.ProverState(zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3), rank, synthetic=True)
     mine = mg.shard_indices(6, rank, world)
     proofs = {i: st.prove(b"assertion-%d" % i, zkw.TRANSCRIPT_EVM, seed=100 + i) for i in mine}
     q.put((rank, ok_msm, {i: p.hex() for i, p in proofs.items()}))
@@ -75,7 +75,7 @@ def test_split_msm_and_sharded_proofs_nccl():
     assert sorted(proofs) == list(range(6)) and len(set(proofs.values())) == 6
     # the same assertion / seed proven on a single GPU gives the same bytes: sharding changes nothing
     zkw = importlib.import_module("webauthn-halo2_b200")
-    st = zkw.ProverState(zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3), 0)
+    st = zkw.ProverState(zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3), 0, synthetic=True)
     try:
         for i in (0, 3, 5):
             assert st.prove(b"assertion-%d" % i, zkw.TRANSCRIPT_EVM, seed=100 + i).hex() == proofs[i]

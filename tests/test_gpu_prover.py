@@ -100,57 +100,77 @@ def test_device_prover_rejects_lookup_input_outside_table(zkw, oracle):
         ctx.close()
 
 
+def _assertion(seed):
+    from tests.assertions import signed_assertion
+    a = signed_assertion(seed)
+    return a, a["pubkey_x"] + a["pubkey_y"] + a["r"] + a["s"] + a["msg_hash"]
+
+
 def test_reference_api_k17_proof_layout_and_acceptance(zkw, oracle):
-    """generate_proof_evm at the server's degree (proving-server/src/main.rs:17): 2720 bytes like the
-    reference's golden proof, accepted by the oracle verifier; invalid inputs raise like the reference panics."""
+    """generate_proof_evm at the server's degree (proving-server/src/main.rs:17) over the REAL ECDSA circuit: 2720 bytes
+    like the reference's golden proof, accepted by the oracle verifier; invalid inputs raise like the reference panics,
+    and a signature that does not verify raises InvalidSignature instead of yielding a proof."""
     from oracle import halo2_ref as h
-    import hashlib
-    x = bytes.fromhex("6b17d1f2e12c4247f8bce6e563a440f277037d812deb33a0f4a13945d898c296")[::-1]   # secp256r1 generator, LE
-    y = bytes.fromhex("4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf51f5")[::-1]
-    r = hashlib.sha256(b"r").digest()[:31] + b"\0"
-    s = hashlib.sha256(b"s").digest()[:31] + b"\0"
-    m = hashlib.sha256(b"m").digest()[:31] + b"\0"
-    proof = zkw.generate_proof_evm(x, y, r, s, m, "./keys/proving_key.pk", 17, seed=5)
+    a, _ = _assertion(17)
+    args = (a["pubkey_x"], a["pubkey_y"], a["r"], a["s"], a["msg_hash"])
+    proof = zkw.generate_proof_evm(*args, "./keys/proving_key.pk", 17, seed=5)
     assert len(proof) == 2720
     st = zkw.download_keys(17, "./keys/proving_key.pk")
+    assert isinstance(st.circuit, zkw.EcdsaCircuit) and not st.synthetic
     oshape = h.Shape(17, 4, 1, 1)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
     assert h.verify_proof(vk, proof, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
     # generate_proof: Blake2b + SHPLONK — 1920 bytes, the size the reference publishes for this config (ecdsa_bench.csv:4)
-    proof_b = zkw.generate_proof(x, y, r, s, m, "./keys/proving_key.pk", 17, seed=5)
+    proof_b = zkw.generate_proof(*args, "./keys/proving_key.pk", 17, seed=5)
     assert len(proof_b) == 1920 and h.verify_proof(vk, proof_b, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
+    x, y, r, s, m = args
     with pytest.raises(ValueError):
         zkw.generate_proof_evm(x, y[:-1] + b"\xff", r, s, m, "./keys/proving_key.pk", 17)     # not on the curve / non-canonical
     with pytest.raises(ValueError):
         zkw.generate_proof_evm(x, y, b"\xff" * 32, s, m, "./keys/proving_key.pk", 17)          # r >= group order
+    bad_m = bytes([m[0] ^ 1]) + m[1:]
+    with pytest.raises(zkw.InvalidSignature):
+        zkw.generate_proof_evm(x, y, r, s, bad_m, "./keys/proving_key.pk", 17)                 # forged: another message hash
+    with pytest.raises(zkw.InvalidSignature):
+        zkw.generate_proof(x, y, s, r, m, "./keys/proving_key.pk", 17)                         # r and s swapped
 
 
 def test_k19_proof_is_accepted(zkw, oracle):
-    """BASELINE config (k = 19, bench_ecdsa.config:1) under the EVM transcript: 15 points + 18 scalars,
-    accepted by the oracle verifier; a corrupted witness yields a proof that is rejected."""
+    """BASELINE config (k = 19, bench_ecdsa.config:1) over the real ECDSA circuit under the EVM transcript: 15 points +
+    18 scalars, accepted by the oracle verifier; the assignment of an INVALID signature (forced through) and a
+    corrupted gate both yield proofs that are rejected."""
     from oracle import halo2_ref as h
     st = zkw.download_keys(19, "k19.pk")
     oshape = h.Shape(19, 1, 0, 1)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
-    proof = st.prove(b"assertion-0", zkw.TRANSCRIPT_EVM, seed=1)
+    a, ab = _assertion(19)
+    proof = st.prove(ab, zkw.TRANSCRIPT_EVM, seed=1)
     assert len(proof) == 15 * 64 + 18 * 32
     assert h.verify_proof(vk, proof, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
     # Blake2b + SHPLONK at k = 19: 960 bytes, the reference's published proof size (ecdsa_bench.csv:2)
-    pb = st.prove(b"assertion-0", zkw.TRANSCRIPT_BLAKE2B, seed=2, shplonk=True)
+    pb = st.prove(ab, zkw.TRANSCRIPT_BLAKE2B, seed=2, shplonk=True)
     assert len(pb) == 960 and h.verify_proof(vk, pb, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
-    adv = st.synthesize(b"assertion-0")
+    adv = st.synthesize(ab)
     adv[0] = adv[0].copy()
-    adv[0][3] = adv[0][7]      # break gate 0: d != a + b*c
+    adv[0][3] = adv[0][7]      # break the first gate of the column
+    bad = zkw.create_proof(st.ctx, st.pk, adv, seed=1, transcript=zkw.TRANSCRIPT_EVM)
+    assert not h.verify_proof(vk, bad, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+    # a forged signature: every relation of the circuit holds except R.x == r (copy constraints)
+    forged = ab[:128] + bytes([ab[128] ^ 1]) + ab[129:]
+    with pytest.raises(zkw.InvalidSignature):
+        st.prove(forged, zkw.TRANSCRIPT_EVM, seed=1)
+    adv = st.synthesize(forged, allow_invalid=True)
     bad = zkw.create_proof(st.ctx, st.pk, adv, seed=1, transcript=zkw.TRANSCRIPT_EVM)
     assert not h.verify_proof(vk, bad, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
 
 
 def test_prover_pool_batch(zkw, oracle):
-    """Independent assertions proven concurrently by several provers on one GPU: every proof verifies,
-    proofs for different assertions differ, and the same (assertion, seed) gives the same bytes on any worker."""
+    """Independent assertions proven concurrently by several provers on one GPU (synthetic test shape at k = 10):
+    every proof verifies, proofs for different assertions differ, and the same (assertion, seed) gives the same bytes
+    on any worker."""
     from oracle import halo2_ref as h
     params = zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3)
-    pool = zkw.ProverPool(params, 0, workers=3)
+    pool = zkw.ProverPool(params, 0, workers=3, synthetic=True)
     try:
         assertions = [b"assertion-%d" % i for i in range(8)] + [b"assertion-0"]
         proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM, seed0=7)
@@ -162,21 +182,38 @@ def test_prover_pool_batch(zkw, oracle):
             assert h.verify_proof(vk, p, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
         again = [s.prove(b"assertion-3", zkw.TRANSCRIPT_EVM, seed=10) for s in pool.states]
         assert again[0] == again[1] == again[2] == proofs[3]
+        # default seeds come from the OS: the same assertion twice gives different proofs
+        p1, p2 = pool.prove_many([b"assertion-1", b"assertion-1"], zkw.TRANSCRIPT_EVM)
+        assert p1 != p2
     finally:
         pool.close()
 
 
-@pytest.mark.parametrize("degree,size", [(16, 3552), (15, 6560), (14, 12704)])
+def test_prover_pool_real_circuit_k17(zkw, oracle):
+    """The batch path on the real ECDSA circuit: four signed assertions over two provers, every proof accepted."""
+    from oracle import halo2_ref as h
+    pool = zkw.ProverPool(zkw.CircuitParams.for_degree(17), 0, workers=2)
+    try:
+        assertions = [_assertion(100 + i)[1] for i in range(4)]
+        proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM)
+        st = pool.states[0]
+        vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(17, 4, 1, 1))
+        assert all(h.verify_proof(vk, p, "evm", tau=zkw.prover.DEV_TAU_CANONICAL) for p in proofs)
+    finally:
+        pool.close()
+
+
+@pytest.mark.parametrize("degree,size", [(18, 1344), (16, 3552), (15, 6560), (14, 12704)])
 def test_proof_sizes_match_reference_csv(zkw, oracle, degree, size):
-    """generate_proof (Blake2b + SHPLONK) for the wider configs of bench_ecdsa.config: the byte counts the
-    reference publishes in halo2-circuits/src/results/ecdsa_bench.csv:5-7, and the proofs verify."""
+    """generate_proof (Blake2b + SHPLONK) over the real ECDSA circuit for the wider configs of bench_ecdsa.config: the
+    byte counts the reference publishes in halo2-circuits/src/results/ecdsa_bench.csv:3,5-7, and the proofs verify."""
     from oracle import halo2_ref as h
     st = zkw.ProverState(zkw.CircuitParams.for_degree(degree), 0)
     try:
         p = st.params
-        proof = st.prove(b"assertion", zkw.TRANSCRIPT_BLAKE2B, seed=3, shplonk=True)
+        proof = st.prove(_assertion(degree)[1], zkw.TRANSCRIPT_BLAKE2B, seed=3, shplonk=True)
         assert len(proof) == size
-        vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(degree, p.num_advice, p.num_lookup_advice, p.num_fixed))
+        vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(degree, p.num_advice, 0 if p.num_advice == 1 else p.num_lookup_advice, p.num_fixed))
         assert h.verify_proof(vk, proof, "blake2b", tau=zkw.prover.DEV_TAU_CANONICAL, multiopen="shplonk")
     finally:
         st.close()
@@ -220,7 +257,6 @@ GY = bytes.fromhex("4fe342e2fe1a7f9b8ee7eb4a7c0f9e162bce33576b315ececbb6406837bf
 
 
 def _k17_evm_device_proof(zkw, oracle):
-    import hashlib
     from oracle import halo2_ref as h
     from tests.assertions import signed_assertion
     a = signed_assertion(17)

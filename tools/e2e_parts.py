@@ -3,7 +3,7 @@ import numpy as np
 sys.path.insert(0, os.getcwd())
 zkw = importlib.import_module("webauthn-halo2_b200")
 st = zkw.ProverState(zkw.CircuitParams.for_degree(19), 0)
-for i in range(3): st.prove(b"w%d" % i, zkw.TRANSCRIPT_EVM, seed=i)
+for i in range(3): st.prove(zkw.synthetic_assertion(i), zkw.TRANSCRIPT_EVM, seed=i)
 stg = st._staging
 ts = []
 for i in range(10):
@@ -15,6 +15,6 @@ for i in range(10):
 print("create_proof(host u64 cols) ms:", [round(x * 1e3, 2) for x in ts])
 ts = []
 for i in range(10):
-    t0 = time.perf_counter(); p = st.prove(b"b%d" % i, zkw.TRANSCRIPT_EVM, seed=i); ts.append(time.perf_counter() - t0)
+    t0 = time.perf_counter(); p = st.prove(zkw.synthetic_assertion(10 + i), zkw.TRANSCRIPT_EVM, seed=i); ts.append(time.perf_counter() - t0)
 print("prove ms:", [round(x * 1e3, 2) for x in ts])
 print(os.cpu_count())

@@ -9,7 +9,8 @@ from .native import (  # noqa: F401
     load_library,
 )
 from .build import build  # noqa: F401
-from .circuit import CircuitParams, SyntheticEcdsaCircuit, validate_assertion  # noqa: F401,E402
+from .circuit import CircuitParams, EcdsaCircuit, InvalidSignature, SyntheticEcdsaCircuit, validate_assertion  # noqa: F401,E402
+from .assertion import synthetic_assertion  # noqa: F401,E402
 from .prover import (  # noqa: F401,E402
     TRANSCRIPT_BLAKE2B, TRANSCRIPT_EVM, ProverPool, ProverState, ProvingKey, create_proof, download_keys, fr_from_mont, fr_to_mont,
     generate_proof, generate_proof_evm, keygen,

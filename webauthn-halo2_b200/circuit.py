@@ -68,6 +68,108 @@ def validate_assertion(pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg
     return tuple(vals)
 
 
+class InvalidSignature(ValueError):
+    """The assertion's (r, s) is not a valid P-256 ECDSA signature of msg_hash under the public key: the circuit has
+    no satisfying assignment, so no proof is attempted."""
+
+
+class EcdsaCircuit:
+    """The P-256 ECDSA verification circuit (ECDSACircuit, ecdsa_p256.rs:65-207) for one config line: layout and
+    witness synthesis live in the library (csrc/ecdsa_circuit.cpp); this class is the host-side handle.
+
+    fixed_columns() / permutation_mapping() feed keygen (the `without_witnesses` pass, ecdsa_p256.rs:90-92,256-260);
+    synthesize() is ECDSACircuit::synthesize (:117-206) for one assertion."""
+
+    def __init__(self, params: CircuitParams):
+        import ctypes as C
+        from . import native
+        self.params = params
+        self._lib = native.load_library()
+        cp = native.CircuitParamsC(params.degree, params.num_advice, params.num_lookup_advice, params.num_fixed, params.lookup_bits,
+                                   params.limb_bits, params.num_limbs)
+        h = C.c_void_p()
+        rc = self._lib.zkw_ecdsa_circuit_new(C.byref(cp), C.byref(h))
+        self._h = h
+        self.shape = native.CircuitShape()
+        if h:
+            self._lib.zkw_ecdsa_circuit_shape(h, C.byref(self.shape))
+        if rc == native.ZKW_ERR_UNSUPPORTED:
+            raise ValueError(f"the ECDSA circuit does not fit config {params} ({self.stats()})")
+        if rc != native.ZKW_OK:
+            raise native.ZkwError(rc, "zkw_ecdsa_circuit_new")
+        self.k, self.n = params.degree, 1 << params.degree
+        self.A, self.F, self.L = self.shape.num_advice, self.shape.num_fixed, self.shape.num_lookup_advice
+        self.selector_mode = self.L == 0
+        self.nfixed = self.F + 1 + self.A + (1 if self.selector_mode else 0)
+        self.nperm = self.F + self.A + self.L
+        self.rows = self._rows()[0]
+
+    def _rows(self):
+        import ctypes as C
+        ncol = self.shape.num_advice + self.shape.num_lookup_advice
+        rows = (C.c_size_t * ncol)()
+        stats = (C.c_uint64 * 4)()
+        self._lib.zkw_ecdsa_circuit_rows(self._h, rows, stats)
+        return [int(x) for x in rows], [int(x) for x in stats]
+
+    def stats(self) -> dict:
+        rows, st = self._rows()
+        return {"rows": rows, "gate_cells": st[0], "lookups": st[1], "constants": st[2], "copies": st[3]}
+
+    def fixed_columns(self) -> list[np.ndarray]:
+        """canonical integers, (n, 4) uint64 each: [constants.., table, q_enable.., (q_lookup)]"""
+        import ctypes as C
+        from . import native
+        cols = [np.zeros((self.n, 4), dtype=np.uint64) for _ in range(self.nfixed)]
+        ptrs = (native.u64p * self.nfixed)(*[c.ctypes.data_as(native.u64p) for c in cols])
+        rc = self._lib.zkw_ecdsa_circuit_fixed(self._h, ptrs)
+        if rc != native.ZKW_OK:
+            raise native.ZkwError(rc, "zkw_ecdsa_circuit_fixed")
+        return cols
+
+    def permutation_mapping(self) -> list[np.ndarray]:
+        import ctypes as C
+        from . import native
+        u32p = C.POINTER(C.c_uint32)
+        maps = [np.zeros((self.n, 2), dtype=np.uint32) for _ in range(self.nperm)]
+        ptrs = (u32p * self.nperm)(*[m.ctypes.data_as(u32p) for m in maps])
+        rc = self._lib.zkw_ecdsa_circuit_permutation(self._h, ptrs)
+        if rc != native.ZKW_OK:
+            raise native.ZkwError(rc, "zkw_ecdsa_circuit_permutation")
+        return maps
+
+    def synthesize(self, pubkey_x: bytes, pubkey_y: bytes, r: bytes, s: bytes, msg_hash: bytes, out: list[np.ndarray] | None = None,
+                   allow_invalid: bool = False) -> list[np.ndarray]:
+        """Advice columns (gate columns, then lookup-advice columns) as (rows, 4) uint64 canonical integers, written
+        into `out` (e.g. views of page-locked memory) or fresh arrays.  Raises InvalidSignature unless the signature
+        verifies (the reference would emit a proof of an unsatisfied system instead, ecdsa_p256.rs:182-191)."""
+        import ctypes as C
+        from . import native
+        if out is None:
+            out = [np.zeros((r_, 4), dtype=np.uint64) for r_ in self.rows]
+        if len(out) != len(self.rows) or any(o.dtype != np.uint64 or o.shape != (r_, 4) or not o.flags.c_contiguous for o, r_ in zip(out, self.rows)):
+            raise ValueError("synthesize: out must be C-contiguous (rows, 4) uint64 arrays, rows = EcdsaCircuit.rows")
+        ptrs = (native.u64p * len(out))(*[o.ctypes.data_as(native.u64p) for o in out])
+        ok = C.c_int(0)
+        rc = self._lib.zkw_ecdsa_synthesize(self._h, bytes(pubkey_x), bytes(pubkey_y), bytes(r), bytes(s), bytes(msg_hash), ptrs, None, C.byref(ok))
+        if rc != native.ZKW_OK:
+            raise native.ZkwError(rc, "zkw_ecdsa_synthesize")
+        if not ok.value and not allow_invalid:
+            raise InvalidSignature("signature does not verify: the ECDSA circuit has no satisfying assignment")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.zkw_ecdsa_circuit_free(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _u64_to_limbs(v: np.ndarray) -> np.ndarray:
     out = np.zeros((v.shape[0], 4), dtype=np.uint64)
     out[:, 0] = v

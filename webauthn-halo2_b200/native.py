@@ -46,6 +46,8 @@ EXPORTS = [
     "zkw_profile_enable", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
     "zkw_keygen", "zkw_pk_destroy", "zkw_pk_info", "zkw_pk_vk", "zkw_create_proof", "zkw_create_proof_ex", "zkw_fr_to_mont", "zkw_fr_from_mont",
     "zkw_synth_witness", "zkw_host_alloc", "zkw_host_free",
+    "zkw_ecdsa_circuit_new", "zkw_ecdsa_circuit_free", "zkw_ecdsa_circuit_shape", "zkw_ecdsa_circuit_rows", "zkw_ecdsa_circuit_fixed",
+    "zkw_ecdsa_circuit_permutation", "zkw_ecdsa_synthesize",
 ]
 
 
@@ -87,6 +89,11 @@ class CircuitShape(C.Structure):
         return self.num_lookup_advice or 1
 
 
+class CircuitParamsC(C.Structure):
+    """zkw_circuit_params: the reference's one-line JSON config (struct CircuitParams, ecdsa_p256.rs:53-63)."""
+    _fields_ = [(n, C.c_uint32) for n in ("degree", "num_advice", "num_lookup_advice", "num_fixed", "lookup_bits", "limb_bits", "num_limbs")]
+
+
 class QuotientInputs(C.Structure):
     _fields_ = [
         ("shape", CircuitShape),
@@ -126,6 +133,16 @@ def load_library() -> C.CDLL:
     lib.zkw_synth_witness.argtypes = [C.POINTER(CircuitShape), C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(u64p), C.POINTER(C.c_size_t)]
     lib.zkw_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkw_host_free.argtypes = [C.c_void_p, C.c_void_p]
+    u8p = C.c_char_p
+    u32p = C.POINTER(C.c_uint32)
+    lib.zkw_ecdsa_circuit_new.argtypes = [C.POINTER(CircuitParamsC), C.POINTER(C.c_void_p)]
+    lib.zkw_ecdsa_circuit_free.argtypes = [C.c_void_p]
+    lib.zkw_ecdsa_circuit_free.restype = None
+    lib.zkw_ecdsa_circuit_shape.argtypes = [C.c_void_p, C.POINTER(CircuitShape)]
+    lib.zkw_ecdsa_circuit_rows.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_uint64)]
+    lib.zkw_ecdsa_circuit_fixed.argtypes = [C.c_void_p, C.POINTER(u64p)]
+    lib.zkw_ecdsa_circuit_permutation.argtypes = [C.c_void_p, C.POINTER(u32p)]
+    lib.zkw_ecdsa_synthesize.argtypes = [C.c_void_p, u8p, u8p, u8p, u8p, u8p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     _lib = lib
     return lib
 

@@ -18,7 +18,7 @@ import os
 import numpy as np
 
 from . import native
-from .circuit import CircuitParams, SyntheticEcdsaCircuit, to_limbs, validate_assertion
+from .circuit import CircuitParams, EcdsaCircuit, InvalidSignature, SyntheticEcdsaCircuit, to_limbs, validate_assertion  # noqa: F401
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -125,36 +125,86 @@ def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, t
 # ---- reference-facing API ------------------------------------------------------------------------------
 class ProverState:
     """Device-resident SRS + proving key for one (degree, config): what the reference keeps on disk as
-    ./params/kzg_bn254_<k>.srs and ./keys/proving_key.pk."""
+    ./params/kzg_bn254_<k>.srs and ./keys/proving_key.pk.
 
-    def __init__(self, params: CircuitParams, device: int = 0, ctx: native.Context | None = None):
+    circuit: the real P-256 ECDSA verification circuit (EcdsaCircuit, csrc/ecdsa_circuit.cpp) by default;
+    synthetic=True selects the shape-identical PRNG-filled test system (SyntheticEcdsaCircuit) — a test shape for
+    sizes the ECDSA circuit cannot fit and for the bit-exact comparison with the Python oracle prover; it attests
+    nothing about a signature and is never reached through generate_proof / generate_proof_evm.
+
+    A state owns one zkw_ctx (stream set, scratch arena, staging columns): prove() is serialised by a lock, so
+    concurrent callers (the reference proves from Rocket worker threads, proving-server/src/main.rs:49-79) queue up
+    on one state; use ProverPool for several provers per GPU."""
+
+    def __init__(self, params: CircuitParams, device: int = 0, ctx: native.Context | None = None, synthetic: bool = False):
+        import threading
         self.params = params
+        self.synthetic = synthetic
         self.ctx = ctx or native.Context(device)
-        self.circuit = SyntheticEcdsaCircuit(params)
-        self.shape = native.CircuitShape.from_config(params.degree, params.num_advice, params.num_lookup_advice, params.num_fixed)
+        self._lock = threading.Lock()
         tau = fr_to_mont(self.ctx, np.array([[(DEV_TAU_CANONICAL >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]], dtype=np.uint64))[0]
         self.ctx.srs_setup(params.degree, tau)                       # gen_srs(degree)
-        fixed = [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.fixed_columns()]
+        if synthetic:
+            self.circuit = SyntheticEcdsaCircuit(params)
+            self.shape = native.CircuitShape.from_config(params.degree, params.num_advice, params.num_lookup_advice, params.num_fixed)
+            fixed = [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.fixed_columns()]
+        else:
+            self.circuit = EcdsaCircuit(params)
+            self.shape = self.circuit.shape
+            fixed = [fr_to_mont(self.ctx, c) for c in self.circuit.fixed_columns()]
         self.pk = keygen(self.ctx, self.shape, fixed, self.circuit.permutation_mapping(), self.circuit)   # keygen_vk + keygen_pk
         self._staging = None
+        self.last_synth_ms = 0.0
 
-    def synthesize(self, assertion: bytes) -> list[np.ndarray]:
-        return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
+    # -- witness -------------------------------------------------------------------------------------
+    def _stage(self):
+        if self._staging is None:
+            if self.synthetic:
+                self._staging = [self.ctx.host_array(r) for r in native.witness_rows(self.shape)]
+            else:
+                self._staging = [self.ctx.host_array(4 * r).reshape(r, 4) for r in self.circuit.rows]
+                for a in self._staging:
+                    a[:] = 0
+        return self._staging
+
+    def synthesize(self, assertion: bytes, allow_invalid: bool = False) -> list[np.ndarray]:
+        """Advice columns in Montgomery form for `assertion` (160 bytes: pubkey_x | pubkey_y | r | s | msg_hash)."""
+        if self.synthetic:
+            return [fr_to_mont(self.ctx, to_limbs(c)) for c in self.circuit.synthesize(assertion)]
+        cols = self.circuit.synthesize(*_split_assertion(assertion), allow_invalid=allow_invalid)
+        return [fr_to_mont(self.ctx, c) for c in cols]
 
     def prove(self, assertion: bytes, transcript: int, seed: int | None = None, shplonk: bool = False) -> bytes:
-        """witness synthesis on the host (zkw_synth_witness, into page-locked staging columns owned by this
-        state), one H2D copy of the canonical advice values, proof bytes back."""
+        """witness synthesis on the host (into page-locked staging columns owned by this state), one H2D copy of the
+        canonical advice values, proof bytes back.  Raises InvalidSignature before any device work when the
+        signature does not verify."""
+        import time
         if seed is None:
             seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
-        if self._staging is None:
-            self._staging = [self.ctx.host_array(r) for r in native.witness_rows(self.shape)]
-        # canonical values < 2^64: shipped as one u64 per row; create_proof returns after the device is done
-        # with the staging columns (the proof bytes depend on them), so the next call may overwrite them
-        cols = native.synth_witness(self.shape, self.params.lookup_bits, assertion, out=self._staging)
-        return create_proof(self.ctx, self.pk, cols, seed, transcript, shplonk=shplonk, u64=True)
+        with self._lock:
+            staging = self._stage()
+            t0 = time.perf_counter()
+            if self.synthetic:
+                # canonical values < 2^64: shipped as one u64 per row
+                cols = native.synth_witness(self.shape, self.params.lookup_bits, assertion, out=staging)
+                self.last_synth_ms = 1e3 * (time.perf_counter() - t0)
+                return create_proof(self.ctx, self.pk, cols, seed, transcript, shplonk=shplonk, u64=True)
+            cols = self.circuit.synthesize(*_split_assertion(assertion), out=staging)
+            self.last_synth_ms = 1e3 * (time.perf_counter() - t0)
+            # create_proof returns after the device is done with the staging columns (the proof bytes depend on
+            # them), so the next call may overwrite them
+            return create_proof(self.ctx, self.pk, cols, seed, transcript, shplonk=shplonk, canonical=True)
 
     def close(self):
         self.pk.close()
+        if not self.synthetic:
+            self.circuit.close()
+
+
+def _split_assertion(assertion: bytes):
+    if len(assertion) != 160:
+        raise ValueError("assertion: expected pubkey_x | pubkey_y | r | s | msg_hash, 5 x 32 little-endian bytes")
+    return tuple(assertion[32 * i: 32 * i + 32] for i in range(5))
 
 
 class ProverPool:
@@ -164,10 +214,12 @@ class ProverPool:
     assertion overlaps the device work of the others, and the latency-bound phases of one proof overlap the
     throughput-bound phases of another."""
 
-    def __init__(self, params: CircuitParams, device: int = 0, workers: int = 3):
-        self.states = [ProverState(params, device) for _ in range(workers)]
+    def __init__(self, params: CircuitParams, device: int = 0, workers: int = 3, synthetic: bool = False):
+        self.states = [ProverState(params, device, synthetic=synthetic) for _ in range(workers)]
 
-    def prove_many(self, assertions: list[bytes], transcript: int, seed0: int = 0) -> list[bytes]:
+    def prove_many(self, assertions: list[bytes], transcript: int, seed0: int | None = None) -> list[bytes]:
+        """seed0 = None (default): every proof draws its own blinding seed from the OS (the reference's OsRng,
+        ecdsa_p256.rs:362); an integer gives the deterministic stream seed0 + i (tests only)."""
         import queue
         import threading
         todo: "queue.Queue[int]" = queue.Queue()
@@ -183,7 +235,7 @@ class ProverPool:
                 except queue.Empty:
                     return
                 try:
-                    out[i] = st.prove(assertions[i], transcript, seed=seed0 + i)
+                    out[i] = st.prove(assertions[i], transcript, seed=None if seed0 is None else seed0 + i)
                 except Exception as e:  # noqa: BLE001 - surfaced below
                     errors.append(e)
                     return
