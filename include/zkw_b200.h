@@ -232,6 +232,13 @@ enum { ZKW_ADVICE_ON_DEVICE = 1, ZKW_ADVICE_CANONICAL = 2, ZKW_MULTIOPEN_SHPLONK
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
                         uint64_t seed, int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* The same with a 256-bit blinding seed (draw it from the OS: upstream uses OsRng, ecdsa_p256.rs:362,412).  Blinding
+ * scalars and the random polynomial come from ChaCha20(seed; nonce = column stream, counter = row), 512 bits per
+ * scalar reduced modulo r.  The 64-bit `seed` of the two entry points above is this seed padded with zeros -
+ * reproducible streams for tests, NOT zero-knowledge. */
+int zkw_create_proof_seeded(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
+                            const uint8_t seed[32], int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+
 /* Host-side witness synthesis for the shape-identical synthetic ECDSA circuit (stands in for
  * ECDSACircuit::synthesize, halo2-circuits/src/ecc/ecdsa_p256.rs:117-206, whose halo2-ecc chips are un-vendored):
  * fills cols_out[c] (c < num_advice: 4 * floor((2^k - blinding_factors - 1) / 4) cells; lookup-advice columns:

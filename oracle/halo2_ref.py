@@ -116,23 +116,43 @@ class Shape:
 # deterministic blinding stream (upstream: OsRng).  element = 254 random bits mod r from splitmix64
 # keyed by (seed, stream, index); mirrored by the device prover so proofs can be compared bit for bit
 # ---------------------------------------------------------------------------------------------------
-_M64 = (1 << 64) - 1
+_M32 = (1 << 32) - 1
 
 
-def _splitmix(z):
-    z = (z + 0x9E3779B97F4A7C15) & _M64
-    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _M64
-    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
-    return z ^ (z >> 31)
+def _rotl32(x, c):
+    return ((x << c) | (x >> (32 - c))) & _M32
 
 
-def rand_fr(seed: int, stream: int, index: int) -> int:
-    base = (seed ^ _splitmix((stream << 32) ^ 0xA5A5A5A5)) & _M64
-    v = 0
-    for j in range(4):
-        v |= _splitmix((base + 4 * index + j) & _M64) << (64 * j)
-    v &= (1 << 254) - 1
-    return v % R
+def _chacha20_block(key_words, stream: int, counter: int):
+    """ChaCha20 block function: 32-byte key (8 words), 64-bit block counter (words 12-13), 64-bit nonce = stream id
+    (words 14-15) — the original 64/64 layout."""
+    s = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + list(key_words) + [counter & _M32, (counter >> 32) & _M32, stream & _M32, (stream >> 32) & _M32]
+    x = list(s)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & _M32; x[d] = _rotl32(x[d] ^ x[a], 16)
+        x[c] = (x[c] + x[d]) & _M32; x[b] = _rotl32(x[b] ^ x[c], 12)
+        x[a] = (x[a] + x[b]) & _M32; x[d] = _rotl32(x[d] ^ x[a], 8)
+        x[c] = (x[c] + x[d]) & _M32; x[b] = _rotl32(x[b] ^ x[c], 7)
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+    return [(x[i] + s[i]) & _M32 for i in range(16)]
+
+
+def seed_words(seed) -> list:
+    """An int seed (< 2^64, the tests' deterministic streams) is the 32-byte key padded with zeros; bytes are the key."""
+    if isinstance(seed, (bytes, bytearray)):
+        assert len(seed) == 32
+        return [int.from_bytes(seed[4 * i: 4 * i + 4], "little") for i in range(8)]
+    return [seed & _M32, (seed >> 32) & _M32, 0, 0, 0, 0, 0, 0]
+
+
+def rand_fr(seed, stream: int, index: int) -> int:
+    """Blinding scalar `index` of column stream `stream`: one ChaCha20 block (512 bits, little-endian) modulo r."""
+    w = _chacha20_block(seed_words(seed), stream, index)
+    return sum(v << (32 * i) for i, v in enumerate(w)) % R
 
 
 STREAM_ADVICE = 1          # + column

@@ -17,8 +17,9 @@ def timed(fn, reps=10):
     b.record(stream); b.synchronize()
     return a.elapsed_time(b) / reps
 msm = timed(lambda: ctx.msm_dev(s, n, zkw.BASES_G))
-cols = st.circuit.synthesize(b"a")
-dev = [torch.from_numpy(zkw.circuit.to_limbs(c).view(np.int64)).cuda() for c in cols]
+_a = zkw.synthetic_assertion(1)
+cols = st.circuit.synthesize(*[_a[32 * j: 32 * j + 32] for j in range(5)])
+dev = [torch.from_numpy(c.view(np.int64)).cuda() for c in cols]
 rows = [c.shape[0] for c in cols]
 i = [0]
 def prove():

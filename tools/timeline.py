@@ -10,8 +10,9 @@ if os.path.exists(out):
 zkw = importlib.import_module("webauthn-halo2_b200")
 st = zkw.ProverState(zkw.CircuitParams.for_degree(degree), 0)
 ctx = st.ctx
-cols = st.circuit.synthesize(b"a")
-dev = [torch.from_numpy(zkw.circuit.to_limbs(c).view(np.int64)).cuda() for c in cols]
+_a = zkw.synthetic_assertion(1)
+cols = st.circuit.synthesize(*[_a[32 * j: 32 * j + 32] for j in range(5)])
+dev = [torch.from_numpy(c.view(np.int64)).cuda() for c in cols]
 rows = [c.shape[0] for c in cols]
 def prove(seed):
     return zkw.create_proof(ctx, st.pk, dev, seed=seed, transcript=zkw.TRANSCRIPT_EVM, canonical=True, device_rows=rows)

@@ -24,9 +24,9 @@ int set_cuda_error(zkw_ctx* ctx, cudaError_t e, const char* what) {
 int ensure_buffer(zkw_ctx* ctx, DeviceBuffer& b, size_t bytes) {
     if (b.bytes >= bytes && b.ptr) return ZKW_OK;
     if (b.ptr) {
-        // the old area may still be in use by queued work
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaStreamSynchronize");
+        // the old area may still be in use by work queued on ANY of the context's streams (main, aux, MSM lanes)
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return set_cuda_error(ctx, e, "cudaDeviceSynchronize");
         cudaFree(b.ptr);
         b.ptr = nullptr;
         b.bytes = 0;
@@ -238,7 +238,13 @@ int zkw_ctx_create(int device, zkw_ctx** out) {
 void zkw_ctx_destroy(zkw_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    // drain every stream of the context (an early error return may have left work queued on the aux stream or the
+    // lanes) and read the timing events back while the streams they were recorded on still exist
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    for (int i = 0; i < zkw_ctx::kMsmLanes; i++)
+        if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
+    profile_collect(ctx);
     for (auto& kv : ctx->twiddles) free_buffer(kv.second);
     for (auto& kv : ctx->staged_twiddles) free_buffer(kv.second);
     free_buffer(ctx->ntt_scratch); free_buffer(ctx->ntt_scratch_aux); free_buffer(ctx->msm_ws);
@@ -248,7 +254,6 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table); free_buffer(ctx->arena);
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    profile_collect(ctx);
     for (int i = 0; i < zkw_ctx::kMsmLanes; i++) {
         free_buffer(ctx->lane_ws[i]);
         if (ctx->lane_pinned[i]) cudaFreeHost(ctx->lane_pinned[i]);

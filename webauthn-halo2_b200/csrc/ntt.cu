@@ -284,6 +284,9 @@ int ntt_get_twiddles(zkw_ctx* ctx, const uint64_t omega[4], unsigned log_n, cons
     const unsigned threads = (count + run - 1) / run;
     { ProfScope ps_(ctx, "twiddle_kernel"); twiddle_kernel<<<(threads + 127) / 128, 128, 0, ctx->stream>>>((uint4*)buf.ptr, fr_from_host(omega), count, run); }
     ZKW_LAUNCHED(ctx);
+    // cold path (once per (omega, log n) and context): the table is built on the main stream but read by whichever
+    // stream the transform runs on (aux stream, MSM lanes' callers), so finish it before anyone can see the pointer
+    ZKW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->twiddles[key] = buf;
     *out_dev = (const uint64_t*)buf.ptr;
     return ZKW_OK;

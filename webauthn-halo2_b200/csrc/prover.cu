@@ -6,8 +6,8 @@
 // (PSE halo2_proofs v2023_01_20 semantics, restated independently in oracle/halo2_ref.py, whose verifier
 // accepts the reference's golden proof).  The host code here only sequences kernels and runs the
 // transcript; every vector stays in HBM from the H2D copy of the witness to the D2H copy of the
-// commitments / evaluations.  Multi-open is GWC for both transcripts (the reference uses SHPLONK with
-// Blake2b; that variant is not built yet — see DESIGN.md).
+// commitments / evaluations.  Multi-open: GWC (generate_proof_evm) or SHPLONK (generate_proof, ZKW_MULTIOPEN_SHPLONK),
+// under either transcript.
 #include <algorithm>
 #include <array>
 #include <cstring>
@@ -264,7 +264,7 @@ static int scan_run(zkw_ctx* ctx, const uint64_t* x, uint64_t* out, size_t n, ui
     return ZKW_OK;
 }
 
-static int rand_fill(zkw_ctx* ctx, uint64_t* out, size_t count, uint64_t seed, uint64_t stream, uint64_t first) {
+static int rand_fill(zkw_ctx* ctx, uint64_t* out, size_t count, const RandKey& seed, uint64_t stream, uint64_t first) {
     if (!count) return ZKW_OK;
     { ProfScope ps_(ctx, "rand_fill_kernel"); rand_fill_kernel<<<grid_for(count, 128), 128, 0, ctx->stream>>>((uint4*)out, count, seed, stream, first); }
     ZKW_LAUNCHED(ctx);
@@ -273,7 +273,7 @@ static int rand_fill(zkw_ctx* ctx, uint64_t* out, size_t count, uint64_t seed, u
 
 // z = grand product over rows: z[0] = *z0 (or 1), z[r] = z0 prod_{i<r} num[i]/den[i] for r <= u, blinding above
 static int grand_product(zkw_ctx* ctx, const uint64_t* num, const uint64_t* den, uint64_t* pn, uint64_t* sd, uint64_t* tmp_blocks,
-                         uint64_t* total_dev, const uint64_t* z0_dev, uint64_t* z, size_t u, size_t n, uint64_t seed, uint64_t stream) {
+                         uint64_t* total_dev, const uint64_t* z0_dev, uint64_t* z, size_t u, size_t n, const RandKey& seed, uint64_t stream) {
     ZKW_TRY((scan_run<true, false>(ctx, num, pn, n, tmp_blocks, nullptr)));
     ZKW_TRY((scan_run<true, true>(ctx, den, sd, n, tmp_blocks, total_dev)));
     Fr total;
@@ -496,16 +496,32 @@ int zkw_pk_vk(const zkw_pk* pk, uint64_t* fixed_commitments_xy, uint64_t* perm_c
 // advice: [A + L] host arrays of advice_rows[c] <= usable rows field elements (Montgomery); the remaining
 // usable rows are zero (unassigned cells), the last blinding_factors+1 rows are blinding.
 // transcript: 0 = Blake2b/Challenge255 (compressed points), 1 = EVM/keccak (uncompressed).
+static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const RandKey& seed,
+                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+
+// 64-bit seeds (deterministic streams for tests and A/B runs) are widened with zeros; production callers pass 32
+// bytes from the OS through zkw_create_proof_seeded
 int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
-                        int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+                        int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
+    RandKey key = {{(uint32_t)seed, (uint32_t)(seed >> 32), 0, 0, 0, 0, 0, 0}};
+    return create_proof_impl(ctx, pk, advice, advice_rows, key, transcript, flags, out, out_cap, out_len);
+}
 
 int zkw_create_proof(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
                      int transcript, uint8_t* out, size_t out_cap, size_t* out_len) {
     return zkw_create_proof_ex(ctx, pk, advice, advice_rows, seed, transcript, 0u, out, out_cap, out_len);
 }
 
-int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, uint64_t seed,
-                        int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
+int zkw_create_proof_seeded(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const uint8_t seed[32],
+                            int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!seed) return ZKW_ERR_INVALID;
+    RandKey key;
+    memcpy(key.w, seed, 32);
+    return create_proof_impl(ctx, pk, advice, advice_rows, key, transcript, flags, out, out_cap, out_len);
+}
+
+static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const RandKey& seed,
+                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
     if (!ctx || !pk || !advice || !advice_rows || !out_len || (transcript != 0 && transcript != 1)) return ZKW_ERR_INVALID;
     const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL, shplonk = flags & ZKW_MULTIOPEN_SHPLONK,
                adv_u64 = flags & ZKW_ADVICE_U64;

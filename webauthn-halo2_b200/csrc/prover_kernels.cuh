@@ -17,31 +17,51 @@ constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
 constexpr int kScanBlock = kScanThreads * kScanPerThread;  // 2048 elements per CTA
 
-// ---- deterministic blinding stream (mirrors oracle/halo2_ref.py::rand_fr) ---------------------------------
-__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ULL;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
+// ---- blinding stream (mirrors oracle/halo2_ref.py::rand_fr) -------------------------------------------------
+// Upstream draws every blinding scalar and the vanishing argument's random polynomial from OsRng
+// (ecdsa_p256.rs:362,412).  Here: ChaCha20 keyed with a 256-bit seed (drawn from the OS by the caller), nonce =
+// the stream id (one stream per blinded column), block counter = the element index.  One 64-byte block gives 512
+// uniform bits, reduced modulo r (bias 2^-258).  A fixed key reproduces a proof bit for bit - what the parity tests
+// against the oracle prover use.
+struct RandKey { uint32_t w[8]; };
 
-__host__ __device__ inline Fr rand_fr(uint64_t seed, uint64_t stream, uint64_t index) {
-    const uint64_t base = seed ^ splitmix64((stream << 32) ^ 0xA5A5A5A5ULL);
-    Fr v;
-    for (int j = 0; j < 4; j++) {
-        uint64_t w = splitmix64(base + 4 * index + j);
-        if (j == 3) w &= 0x3FFFFFFFFFFFFFFFULL;
-        v.l[2 * j] = (uint32_t)w;
-        v.l[2 * j + 1] = (uint32_t)(w >> 32);
+__host__ __device__ inline uint32_t rotl32(uint32_t x, int c) { return (x << c) | (x >> (32 - c)); }
+
+__host__ __device__ inline void chacha20_block(const RandKey& key, uint64_t stream, uint64_t counter, uint32_t out[16]) {
+    uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key.w[0], key.w[1], key.w[2], key.w[3],
+                      key.w[4], key.w[5], key.w[6], key.w[7], (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = s[i];
+#define ZKW_QR(a, b, c, d)                                                                                             \
+    x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);                        \
+    x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+#pragma unroll 1
+    for (int r = 0; r < 10; r++) {
+        ZKW_QR(0, 4, 8, 12) ZKW_QR(1, 5, 9, 13) ZKW_QR(2, 6, 10, 14) ZKW_QR(3, 7, 11, 15)
+        ZKW_QR(0, 5, 10, 15) ZKW_QR(1, 6, 11, 12) ZKW_QR(2, 7, 8, 13) ZKW_QR(3, 4, 9, 14)
     }
-    v.reduce_once();  // < 2^254 < 2r
-    return v.to_mont();
+#undef ZKW_QR
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
 }
 
-__global__ void rand_fill_kernel(uint4* out, size_t count, uint64_t seed, uint64_t stream, uint64_t first_index) {
+// (lo + 2^256 hi) mod r in Montgomery form, lo = words 0..7, hi = words 8..15 (little-endian)
+__host__ __device__ inline Fr rand_fr(const RandKey& key, uint64_t stream, uint64_t index) {
+    uint32_t b[16];
+    chacha20_block(key, stream, index, b);
+    Fr lo, hi;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { lo.l[j] = b[j]; hi.l[j] = b[8 + j]; }
+    for (int j = 0; j < 5; j++) { lo.reduce_once(); hi.reduce_once(); }   // 2^256 < 6r
+    const Fr r2 = Fr::r2();
+    return lo * r2 + hi * (r2 * r2);      // lo R + hi R^2 (mod r) = Montgomery form of lo + hi 2^256
+}
+
+__global__ void rand_fill_kernel(uint4* out, size_t count, RandKey key, uint64_t stream, uint64_t first_index) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    rand_fr(seed, stream, first_index + i).store(out + 2 * i);
+    rand_fr(key, stream, first_index + i).store(out + 2 * i);
 }
 
 __global__ void zero_fill_kernel(uint4* out, size_t count) {

@@ -61,6 +61,8 @@ def _bind(lib):
                                      C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.zkw_create_proof_ex.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_uint64, C.c_int, C.c_uint,
                                         C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.zkw_create_proof_seeded.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.c_char_p, C.c_int, C.c_uint,
+                                            C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
     lib.zkw_fr_to_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
     lib.zkw_fr_from_mont.argtypes = [C.c_void_p, u64p, u64p, C.c_size_t]
 
@@ -97,12 +99,13 @@ ADVICE_ON_DEVICE, ADVICE_CANONICAL, MULTIOPEN_SHPLONK, ADVICE_U64 = 1, 2, 4, 8
 _PROOF_CAP = 1 << 20
 
 
-def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, transcript: int, *, canonical: bool = False,
+def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed, transcript: int, *, canonical: bool = False,
                  device_rows: list[int] | None = None, shplonk: bool = False, u64: bool = False) -> bytes:
     """create_proof on the device.  advice: one (rows, 4) uint64 array per advice column — host numpy arrays,
     or (with device_rows given) device tensors / addresses.  canonical=True: values are plain integers that
     the device converts to Montgomery form; u64=True: one uint64 per row ((rows,) arrays), widened on the device.  shplonk=True: SHPLONK multi-open (the reference's generate_proof)
-    instead of GWC (generate_proof_evm)."""
+    instead of GWC (generate_proof_evm).  seed: 32 bytes (from the OS: the blinding is then zero-knowledge) or an int
+    below 2^64 (a reproducible stream for tests)."""
     _bind(ctx.lib)
     flags = (ADVICE_CANONICAL if canonical else 0) | (MULTIOPEN_SHPLONK if shplonk else 0) | (ADVICE_U64 if u64 else 0)
     if device_rows is not None:
@@ -116,8 +119,14 @@ def create_proof(ctx: native.Context, pk: ProvingKey, advice: list, seed: int, t
         rows = (C.c_size_t * len(keep))(*[a.shape[0] for a in keep])
     buf = (C.c_uint8 * _PROOF_CAP)()
     n = C.c_size_t(0)
-    ctx._check(ctx.lib.zkw_create_proof_ex(ctx.h, pk.h, at, rows, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), transcript, flags, buf, _PROOF_CAP,
-                                           C.byref(n)), "zkw_create_proof_ex")
+    if isinstance(seed, (bytes, bytearray)):
+        if len(seed) != 32:
+            raise ValueError("seed: expected 32 bytes")
+        ctx._check(ctx.lib.zkw_create_proof_seeded(ctx.h, pk.h, at, rows, bytes(seed), transcript, flags, buf, _PROOF_CAP, C.byref(n)),
+                   "zkw_create_proof_seeded")
+    else:
+        ctx._check(ctx.lib.zkw_create_proof_ex(ctx.h, pk.h, at, rows, C.c_uint64(seed & 0xFFFFFFFFFFFFFFFF), transcript, flags, buf, _PROOF_CAP,
+                                               C.byref(n)), "zkw_create_proof_ex")
     del keep
     return bytes(buf[: n.value])
 
@@ -174,13 +183,13 @@ class ProverState:
         cols = self.circuit.synthesize(*_split_assertion(assertion), allow_invalid=allow_invalid)
         return [fr_to_mont(self.ctx, c) for c in cols]
 
-    def prove(self, assertion: bytes, transcript: int, seed: int | None = None, shplonk: bool = False) -> bytes:
+    def prove(self, assertion: bytes, transcript: int, seed=None, shplonk: bool = False) -> bytes:
         """witness synthesis on the host (into page-locked staging columns owned by this state), one H2D copy of the
         canonical advice values, proof bytes back.  Raises InvalidSignature before any device work when the
         signature does not verify."""
         import time
         if seed is None:
-            seed = int.from_bytes(os.urandom(8), "little")           # the reference draws blinding from OsRng
+            seed = os.urandom(32)                                    # the reference draws blinding from OsRng (ecdsa_p256.rs:362)
         with self._lock:
             staging = self._stage()
             t0 = time.perf_counter()
