@@ -51,7 +51,8 @@ typedef enum {
     ZKW_ERR_INVALID = -3,     /* bad argument (NULL, size not a power of two, k out of range …) */
     ZKW_ERR_OOM = -4,         /* device allocation failed */
     ZKW_ERR_STATE = -5,       /* e.g. MSM against SRS bases before zkw_srs_load */
-    ZKW_ERR_UNSUPPORTED = -6  /* circuit shape outside what the quotient kernel was built for */
+    ZKW_ERR_UNSUPPORTED = -6, /* circuit shape outside what the quotient kernel was built for */
+    ZKW_ERR_SIGNATURE = -7    /* the assertion's signature does not verify: the ECDSA circuit has no satisfying assignment */
 } zkw_status;
 
 /* ---- context ------------------------------------------------------------------------- */
@@ -215,6 +216,17 @@ int zkw_pk_info(const zkw_pk* pk, uint32_t* num_fixed_cols, uint32_t* num_perm_c
  * pinned VK): Blake2b-512("Halo2-Verify-Key") over a canonical serialisation, mod r. */
 int zkw_pk_vk(const zkw_pk* pk, uint64_t* fixed_commitments_xy, uint64_t* perm_commitments_xy, uint64_t digest[4]);
 
+/* Key files: ProvingKey / VerifyingKey ::to_bytes(SerdeFormat::RawBytes) + ::read (ecdsa_p256.rs:261-270 writes them in
+ * download_keys, :339-343 and :388-393 read the proving key on every request, :280-284 the verifying key).  Raw bytes
+ * = in-memory Montgomery limbs.  The proving-key file starts with the verifying key (shape, digest, commitments),
+ * followed by values + polynomial of every fixed and permutation column; extended cosets are recomputed on load (one
+ * NTT each).  zkw_pk_read needs the resident SRS of the same size.  zkw_vk_read accepts either file. */
+int zkw_pk_write(zkw_ctx* ctx, const zkw_pk* pk, const char* path);
+int zkw_pk_read(zkw_ctx* ctx, const char* path, zkw_pk** out);
+int zkw_vk_write(const zkw_pk* pk, const char* path);
+int zkw_vk_read(const char* path, zkw_circuit_shape* shape, uint32_t* num_fixed_cols, uint32_t* num_perm_cols,
+                uint64_t* fixed_commitments_xy, size_t fixed_cap, uint64_t* perm_commitments_xy, size_t perm_cap, uint64_t digest[4]);
+
 enum { ZKW_TRANSCRIPT_BLAKE2B = 0, ZKW_TRANSCRIPT_EVM = 1 };
 /* advice: [num_advice + num_lookup_advice] host arrays holding the first advice_rows[c] (<= n - 7)
  * rows of each advice column (Montgomery); unassigned usable rows are zero, the last
@@ -276,6 +288,31 @@ int zkw_ecdsa_circuit_permutation(const zkw_ecdsa_circuit* c, uint32_t* const* m
 int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pubkey_x[32], const uint8_t pubkey_y[32], const uint8_t r[32],
                          const uint8_t s[32], const uint8_t msg_hash[32], uint64_t* const* advice_out, size_t* rows_out,
                          int* signature_ok);
+
+/* ---- the resident prover: download_keys + generate_proof{,_evm} + the server's concurrent requests ------------------
+ * zkw_prover_create = download_keys(degree, pk_path, vk_path) (ecdsa_p256.rs:256-272) kept resident: context on
+ * `device`, development SRS for `tau` (Montgomery; gen_srs), the ECDSA circuit for `params`, and the proving key —
+ * read from pk_path when that file exists (ProvingKey::read, :339-343), else generated and, when pk_path / vk_path are
+ * given, written there (:261-270).  One prover proves one assertion at a time (internally locked). */
+typedef struct zkw_prover zkw_prover;
+int zkw_prover_create(int device, const zkw_circuit_params* params, const uint64_t tau[4], const char* pk_path, const char* vk_path,
+                      zkw_prover** out);
+void zkw_prover_destroy(zkw_prover* p);
+zkw_ctx* zkw_prover_ctx(zkw_prover* p);
+const zkw_pk* zkw_prover_pk(zkw_prover* p);
+double zkw_prover_last_synthesis_ms(zkw_prover* p);
+/* generate_proof_evm (transcript EVM, flags 0: GWC; ecdsa_p256.rs:329-377) / generate_proof (transcript BLAKE2B, flags
+ * ZKW_MULTIOPEN_SHPLONK; :379-427) for one assertion = pubkey_x | pubkey_y | r | s | msg_hash, 5 x 32 little-endian bytes.
+ * seed32_or_null: NULL draws the blinding seed from the OS.  ZKW_ERR_INVALID for non-canonical encodings (the reference
+ * panics on from_bytes().unwrap()), ZKW_ERR_SIGNATURE when the signature does not verify (nothing is proven). */
+int zkw_prover_prove(zkw_prover* p, const uint8_t assertion[160], const uint8_t* seed32_or_null, int transcript, unsigned flags,
+                     uint8_t* out, size_t out_cap, size_t* out_len);
+/* A batch of independent assertions over `nworkers` provers (same or different GPUs), one host thread per prover pulling
+ * from a shared queue: witness synthesis of one proof overlaps the device work of the others.  proofs: count slots of
+ * proof_stride bytes; proof_lens[i] = 0 and statuses[i] (may be NULL) = the error for assertions that failed.  Returns
+ * the first error, ZKW_OK if every proof was made. */
+int zkw_prove_batch(zkw_prover* const* workers, size_t nworkers, const uint8_t* assertions, size_t count, const uint8_t* seeds32_or_null,
+                    int transcript, unsigned flags, uint8_t* proofs, size_t proof_stride, size_t* proof_lens, int* statuses);
 
 /* Fr vectors between canonical little-endian integers (< 2r accepted) and halo2curves' Montgomery form;
  * host pointers, n elements of 4 u64. */

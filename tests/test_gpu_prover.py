@@ -115,7 +115,7 @@ def test_reference_api_k17_proof_layout_and_acceptance(zkw, oracle):
     args = (a["pubkey_x"], a["pubkey_y"], a["r"], a["s"], a["msg_hash"])
     proof = zkw.generate_proof_evm(*args, "./keys/proving_key.pk", 17, seed=5)
     assert len(proof) == 2720
-    st = zkw.download_keys(17, "./keys/proving_key.pk")
+    st = zkw.prover._state_for(17, "./keys/proving_key.pk", 0)
     assert isinstance(st.circuit, zkw.EcdsaCircuit) and not st.synthetic
     oshape = h.Shape(17, 4, 1, 1)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
@@ -140,7 +140,7 @@ def test_k19_proof_is_accepted(zkw, oracle):
     18 scalars, accepted by the oracle verifier; the assignment of an INVALID signature (forced through) and a
     corrupted gate both yield proofs that are rejected."""
     from oracle import halo2_ref as h
-    st = zkw.download_keys(19, "k19.pk")
+    st = zkw.prover._state_for(19, "k19.pk", 0)
     oshape = h.Shape(19, 1, 0, 1)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, oshape)
     a, ab = _assertion(19)
@@ -162,6 +162,46 @@ def test_k19_proof_is_accepted(zkw, oracle):
     adv = st.synthesize(forged, allow_invalid=True)
     bad = zkw.create_proof(st.ctx, st.pk, adv, seed=1, transcript=zkw.TRANSCRIPT_EVM)
     assert not h.verify_proof(vk, bad, "evm", tau=zkw.prover.DEV_TAU_CANONICAL)
+
+
+def test_key_files_round_trip(zkw, oracle, tmp_path):
+    """download_keys writes the proving and verifying key files (ecdsa_p256.rs:256-272: to_bytes(RawBytes)); a prover that
+    READS the proving key (ProvingKey::read, :339-343) makes byte-identical proofs to the one that generated it, the
+    verifying-key file holds the same commitments and digest, and a damaged file is an error, not a crash."""
+    pk_path, vk_path = str(tmp_path / "keys" / "proving_key.pk"), str(tmp_path / "keys" / "verifying_key.vk")
+    st = zkw.download_keys(15, pk_path, vk_path)
+    try:
+        import os
+        assert os.path.getsize(pk_path) > 2 * (1 << 15) * 32 and os.path.getsize(vk_path) < 1 << 16
+        fx, pm, dg = st.pk.vk()
+        shape, vfx, vpm, vdg, counts = zkw.prover.read_vk(vk_path)
+        assert (shape.k, shape.num_advice, shape.num_lookup_advice) == (15, 17, 3) and counts == (fx.shape[0], pm.shape[0])
+        assert np.array_equal(vfx, fx) and np.array_equal(vpm, pm) and np.array_equal(vdg, dg)
+        _, pfx, _, pdg, _ = zkw.prover.read_vk(pk_path)           # the proving-key file starts with the verifying key
+        assert np.array_equal(pfx, fx) and np.array_equal(pdg, dg)
+        _, ab = _assertion(15)
+        want = st.prove(ab, zkw.TRANSCRIPT_EVM, seed=9)
+        st2 = zkw.ProverState(zkw.CircuitParams.for_degree(15), 0, proving_key_path=pk_path)     # reads the file
+        try:
+            assert st2.prove(ab, zkw.TRANSCRIPT_EVM, seed=9) == want
+            assert st2.prove(ab, zkw.TRANSCRIPT_BLAKE2B, seed=9, shplonk=True) == st.prove(ab, zkw.TRANSCRIPT_BLAKE2B, seed=9, shplonk=True)
+        finally:
+            st2.close()
+        # generate_proof_evm with that path picks the file up (and keeps the key resident afterwards)
+        a, _ = _assertion(15)
+        got = zkw.generate_proof_evm(a["pubkey_x"], a["pubkey_y"], a["r"], a["s"], a["msg_hash"], pk_path, 15, seed=9)
+        assert got == want
+        with open(pk_path, "r+b") as f:
+            f.truncate(os.path.getsize(pk_path) // 2)
+        with pytest.raises(zkw.ZkwError):
+            zkw.ProverState(zkw.CircuitParams.for_degree(15), 0, proving_key_path=pk_path)
+        with open(vk_path, "r+b") as f:
+            f.write(b"garbage!")
+        with pytest.raises(zkw.ZkwError):
+            zkw.prover.read_vk(vk_path)
+    finally:
+        zkw.prover._STATES.pop((15, pk_path, 0), None)
+        st.close()
 
 
 def test_prover_pool_batch(zkw, oracle):
@@ -261,7 +301,7 @@ def _k17_evm_device_proof(zkw, oracle):
     from tests.assertions import signed_assertion
     a = signed_assertion(17)
     proof = zkw.generate_proof_evm(a["pubkey_x"], a["pubkey_y"], a["r"], a["s"], a["msg_hash"], "./keys/proving_key.pk", 17, seed=5)
-    st = zkw.download_keys(17, "./keys/proving_key.pk")
+    st = zkw.prover._state_for(17, "./keys/proving_key.pk", 0)
     vk = _oracle_vk(zkw, oracle, st.ctx, st.pk, h.Shape(17, 4, 1, 1))
     return proof, vk
 

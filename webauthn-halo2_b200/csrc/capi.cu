@@ -206,6 +206,7 @@ const char* zkw_strerror(int status) {
         case ZKW_ERR_OOM: return "out of device memory";
         case ZKW_ERR_STATE: return "invalid state (SRS not loaded?)";
         case ZKW_ERR_UNSUPPORTED: return "unsupported circuit shape";
+        case ZKW_ERR_SIGNATURE: return "signature does not verify (the ECDSA circuit has no satisfying assignment)";
         default: return "unknown status";
     }
 }

@@ -320,6 +320,75 @@ void zkw_pk_destroy(zkw_ctx* ctx, zkw_pk* pk) {
 
 // fixed_values: [F constants, table, A gate selectors, (q_lookup)] each n*4 u64 Montgomery (host);
 // perm_mapping: [F + A + L] each n (col', row') u32 pairs (host) — halo2's keygen Assembly mapping.
+// What both keygen and zkw_pk_read derive from the columns: l_0 / l_last / l_active on the extended coset and the
+// sorted lookup table with multiplicities.  table_host: the table column's n values (Montgomery, host).
+static int pk_derived(zkw_ctx* ctx, zkw_pk* pkp, const Domain& dom, const uint64_t* table_host) {
+    struct Holder { zkw_pk* p; zkw_pk* get() const { return p; } zkw_pk* operator->() const { return p; } } pk{pkp};
+    const zkw_circuit_shape& sh = pkp->shape;
+    const size_t n = pkp->n, vb = n * 32, eb = pkp->en * 32;
+    cudaStream_t st = ctx->stream;
+    const uint64_t* const fixed_table = table_host;
+    // l0, l_last, l_active on the extended coset
+    {
+        std::vector<uint64_t> h(n * 4, 0);
+        Fr one = Fr::one();
+        Scratch sc(ctx);
+        uint64_t *d_v, *d_poly_unused;
+        ZKW_TRY(sc.get(vb, (void**)&d_v));
+        auto make = [&](uint64_t** coset) -> int {
+            ZKW_CUDA(ctx, cudaMemcpyAsync(d_v, h.data(), vb, cudaMemcpyHostToDevice, st));
+            ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+            ZKW_TRY(dmalloc(ctx, pk.get(), eb, (void**)coset));
+            ZKW_TRY(ntt_run(ctx, d_v, sh.k, d_v, sh.k, dom.dc.omega_inv, false, dom.dc.n_scale3));
+            return ntt_run(ctx, d_v, sh.k, *coset, sh.ext_k, dom.dc.ext_omega, true, nullptr);
+        };
+        (void)d_poly_unused;
+        memcpy(&h[0], one.l, 32);
+        ZKW_TRY(make(&pk->l0_coset));
+        std::fill(h.begin(), h.end(), 0);
+        memcpy(&h[4 * pk->u], one.l, 32);
+        ZKW_TRY(make(&pk->l_last_coset));
+        std::fill(h.begin(), h.end(), 0);
+        for (size_t i = 0; i < pk->u; i++) memcpy(&h[4 * i], one.l, 32);
+        ZKW_TRY(make(&pk->l_active_coset));
+    }
+    // lookup table: sorted distinct values over the usable rows, with multiplicities (host sort, keygen time)
+    {
+        const uint64_t* tab = fixed_table;
+        std::vector<std::array<uint64_t, 4>> canon(pk->u);
+        for (size_t i = 0; i < pk->u; i++) {
+            Fr v; memcpy(v.l, tab + 4 * i, 32);
+            v = v.from_mont();
+            memcpy(canon[i].data(), v.l, 32);
+        }
+        auto less = [](const std::array<uint64_t, 4>& a, const std::array<uint64_t, 4>& b) {
+            for (int i = 3; i >= 0; i--) if (a[i] != b[i]) return a[i] < b[i];
+            return false;
+        };
+        std::sort(canon.begin(), canon.end(), less);
+        std::vector<uint64_t> vals_c, vals_m;
+        std::vector<uint32_t> mult;
+        for (size_t i = 0; i < canon.size(); i++) {
+            if (i && canon[i] == canon[i - 1]) { mult.back()++; continue; }
+            vals_c.insert(vals_c.end(), canon[i].begin(), canon[i].end());
+            Fr v; memcpy(v.l, canon[i].data(), 32);
+            v = v.to_mont();
+            uint64_t m4[4]; memcpy(m4, v.l, 32);
+            vals_m.insert(vals_m.end(), m4, m4 + 4);
+            mult.push_back(1);
+        }
+        pk->table_m = (uint32_t)mult.size();
+        ZKW_TRY(dmalloc(ctx, pk.get(), vals_c.size() * 8, (void**)&pk->table_canon));
+        ZKW_TRY(dmalloc(ctx, pk.get(), vals_m.size() * 8, (void**)&pk->table_mont));
+        ZKW_TRY(dmalloc(ctx, pk.get(), mult.size() * 4, (void**)&pk->table_mult));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_canon, vals_c.data(), vals_c.size() * 8, cudaMemcpyHostToDevice, st));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_mont, vals_m.data(), vals_m.size() * 8, cudaMemcpyHostToDevice, st));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_mult, mult.data(), mult.size() * 4, cudaMemcpyHostToDevice, st));
+        ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return ZKW_OK;
+}
+
 int zkw_keygen(zkw_ctx* ctx, const zkw_circuit_shape* shape, const uint64_t* const* fixed_values, const uint32_t* const* perm_mapping,
                zkw_pk** out) {
     if (!ctx || !shape || !fixed_values || !perm_mapping || !out) return ZKW_ERR_INVALID;
@@ -395,64 +464,7 @@ int zkw_keygen(zkw_ctx* ctx, const zkw_circuit_shape* shape, const uint64_t* con
             ZKW_TRY(to_poly_and_coset(pk->sigma_values[c], &pk->sigma_polys[c], &pk->sigma_cosets[c]));
         }
     }
-    // l0, l_last, l_active on the extended coset
-    {
-        std::vector<uint64_t> h(n * 4, 0);
-        Fr one = Fr::one();
-        Scratch sc(ctx);
-        uint64_t *d_v, *d_poly_unused;
-        ZKW_TRY(sc.get(vb, (void**)&d_v));
-        auto make = [&](uint64_t** coset) -> int {
-            ZKW_CUDA(ctx, cudaMemcpyAsync(d_v, h.data(), vb, cudaMemcpyHostToDevice, st));
-            ZKW_CUDA(ctx, cudaStreamSynchronize(st));
-            ZKW_TRY(dmalloc(ctx, pk.get(), eb, (void**)coset));
-            ZKW_TRY(ntt_run(ctx, d_v, sh.k, d_v, sh.k, dom.dc.omega_inv, false, dom.dc.n_scale3));
-            return ntt_run(ctx, d_v, sh.k, *coset, sh.ext_k, dom.dc.ext_omega, true, nullptr);
-        };
-        (void)d_poly_unused;
-        memcpy(&h[0], one.l, 32);
-        ZKW_TRY(make(&pk->l0_coset));
-        std::fill(h.begin(), h.end(), 0);
-        memcpy(&h[4 * pk->u], one.l, 32);
-        ZKW_TRY(make(&pk->l_last_coset));
-        std::fill(h.begin(), h.end(), 0);
-        for (size_t i = 0; i < pk->u; i++) memcpy(&h[4 * i], one.l, 32);
-        ZKW_TRY(make(&pk->l_active_coset));
-    }
-    // lookup table: sorted distinct values over the usable rows, with multiplicities (host sort, keygen time)
-    {
-        const uint64_t* tab = fixed_values[pk->table_col()];
-        std::vector<std::array<uint64_t, 4>> canon(pk->u);
-        for (size_t i = 0; i < pk->u; i++) {
-            Fr v; memcpy(v.l, tab + 4 * i, 32);
-            v = v.from_mont();
-            memcpy(canon[i].data(), v.l, 32);
-        }
-        auto less = [](const std::array<uint64_t, 4>& a, const std::array<uint64_t, 4>& b) {
-            for (int i = 3; i >= 0; i--) if (a[i] != b[i]) return a[i] < b[i];
-            return false;
-        };
-        std::sort(canon.begin(), canon.end(), less);
-        std::vector<uint64_t> vals_c, vals_m;
-        std::vector<uint32_t> mult;
-        for (size_t i = 0; i < canon.size(); i++) {
-            if (i && canon[i] == canon[i - 1]) { mult.back()++; continue; }
-            vals_c.insert(vals_c.end(), canon[i].begin(), canon[i].end());
-            Fr v; memcpy(v.l, canon[i].data(), 32);
-            v = v.to_mont();
-            uint64_t m4[4]; memcpy(m4, v.l, 32);
-            vals_m.insert(vals_m.end(), m4, m4 + 4);
-            mult.push_back(1);
-        }
-        pk->table_m = (uint32_t)mult.size();
-        ZKW_TRY(dmalloc(ctx, pk.get(), vals_c.size() * 8, (void**)&pk->table_canon));
-        ZKW_TRY(dmalloc(ctx, pk.get(), vals_m.size() * 8, (void**)&pk->table_mont));
-        ZKW_TRY(dmalloc(ctx, pk.get(), mult.size() * 4, (void**)&pk->table_mult));
-        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_canon, vals_c.data(), vals_c.size() * 8, cudaMemcpyHostToDevice, st));
-        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_mont, vals_m.data(), vals_m.size() * 8, cudaMemcpyHostToDevice, st));
-        ZKW_CUDA(ctx, cudaMemcpyAsync(pk->table_mult, mult.data(), mult.size() * 4, cudaMemcpyHostToDevice, st));
-        ZKW_CUDA(ctx, cudaStreamSynchronize(st));
-    }
+    ZKW_TRY(pk_derived(ctx, pk.get(), dom, fixed_values[pk->table_col()]));
     // VK digest (self-defined, see oracle/halo2_ref.py::vk_digest): Blake2b-512("Halo2-Verify-Key") mod r
     {
         Blake2b h(64, "Halo2-Verify-Key");
@@ -490,6 +502,147 @@ int zkw_pk_vk(const zkw_pk* pk, uint64_t* fixed_commitments_xy, uint64_t* perm_c
     if (fixed_commitments_xy) for (unsigned c = 0; c < pk->nfixed; c++) memcpy(fixed_commitments_xy + 8 * c, pk->fixed_commitments[c].data(), 64);
     if (perm_commitments_xy) for (unsigned c = 0; c < pk->nperm; c++) memcpy(perm_commitments_xy + 8 * c, pk->perm_commitments[c].data(), 64);
     if (digest) memcpy(digest, pk->digest, 32);
+    return ZKW_OK;
+}
+
+// ---- key files: the replacement of ProvingKey / VerifyingKey ::to_bytes / ::read with SerdeFormat::RawBytes -------
+// (ecdsa_p256.rs:261-270 writes them in download_keys, :339-343 / :388-393 read the proving key on every request).
+// "Raw bytes" = the in-memory Montgomery limbs, as upstream's RawBytes.  Layout (little-endian):
+//   magic "ZKWPK1\0\0" | zkw_circuit_shape (8 u32) | nfixed u32 | nperm u32 | digest 32 B
+//   | fixed commitments nfixed x 64 B | permutation commitments nperm x 64 B            <- the verifying key ends here
+//   | per fixed column: values n x 32 B, polynomial n x 32 B | per permutation column: sigma values, sigma polynomial
+// Extended cosets, l_0 / l_last / l_active and the sorted lookup table are NOT stored (upstream stores the cosets):
+// they are one NTT each on load, which is faster than reading 4n more field elements per column from disk.
+static const char kPkMagic[8] = {'Z', 'K', 'W', 'P', 'K', '1', 0, 0};
+static const char kVkMagic[8] = {'Z', 'K', 'W', 'V', 'K', '1', 0, 0};
+
+static int write_vk_part(FILE* f, const zkw_pk* pk, const char magic[8]) {
+    const uint32_t counts[2] = {pk->nfixed, pk->nperm};
+    if (fwrite(magic, 1, 8, f) != 8 || fwrite(&pk->shape, sizeof(zkw_circuit_shape), 1, f) != 1 || fwrite(counts, 4, 2, f) != 2 ||
+        fwrite(pk->digest, 8, 4, f) != 4)
+        return ZKW_ERR_INVALID;
+    for (auto& c : pk->fixed_commitments) if (fwrite(c.data(), 8, 8, f) != 8) return ZKW_ERR_INVALID;
+    for (auto& c : pk->perm_commitments) if (fwrite(c.data(), 8, 8, f) != 8) return ZKW_ERR_INVALID;
+    return ZKW_OK;
+}
+
+int zkw_vk_write(const zkw_pk* pk, const char* path) {
+    if (!pk || !path) return ZKW_ERR_INVALID;
+    FILE* f = fopen(path, "wb");
+    if (!f) return ZKW_ERR_INVALID;
+    int rc = write_vk_part(f, pk, kVkMagic);
+    if (fclose(f) != 0) rc = ZKW_ERR_INVALID;
+    return rc;
+}
+
+int zkw_vk_read(const char* path, zkw_circuit_shape* shape, uint32_t* num_fixed_cols, uint32_t* num_perm_cols, uint64_t* fixed_commitments_xy,
+                size_t fixed_cap, uint64_t* perm_commitments_xy, size_t perm_cap, uint64_t digest[4]) {
+    if (!path) return ZKW_ERR_INVALID;
+    FILE* f = fopen(path, "rb");
+    if (!f) return ZKW_ERR_INVALID;
+    char magic[8];
+    zkw_circuit_shape sh;
+    uint32_t counts[2];
+    uint64_t dg[4];
+    int rc = ZKW_OK;
+    if (fread(magic, 1, 8, f) != 8 || (memcmp(magic, kVkMagic, 8) && memcmp(magic, kPkMagic, 8)) || fread(&sh, sizeof sh, 1, f) != 1 ||
+        fread(counts, 4, 2, f) != 2 || fread(dg, 8, 4, f) != 4)
+        rc = ZKW_ERR_INVALID;
+    if (rc == ZKW_OK) {
+        if (shape) *shape = sh;
+        if (num_fixed_cols) *num_fixed_cols = counts[0];
+        if (num_perm_cols) *num_perm_cols = counts[1];
+        if (digest) memcpy(digest, dg, 32);
+        std::vector<uint64_t> pts(8 * ((size_t)counts[0] + counts[1]));
+        if (counts[0] > 4096 || counts[1] > 4096 || fread(pts.data(), 8, pts.size(), f) != pts.size()) rc = ZKW_ERR_INVALID;
+        else {
+            if (fixed_commitments_xy) { if (fixed_cap < counts[0]) rc = ZKW_ERR_INVALID; else memcpy(fixed_commitments_xy, pts.data(), 64 * (size_t)counts[0]); }
+            if (perm_commitments_xy) { if (perm_cap < counts[1]) rc = ZKW_ERR_INVALID; else memcpy(perm_commitments_xy, pts.data() + 8 * (size_t)counts[0], 64 * (size_t)counts[1]); }
+        }
+    }
+    fclose(f);
+    return rc;
+}
+
+int zkw_pk_write(zkw_ctx* ctx, const zkw_pk* pk, const char* path) {
+    if (!ctx || !pk || !path) return ZKW_ERR_INVALID;
+    ZKW_CUDA(ctx, cudaSetDevice(ctx->device));
+    FILE* f = fopen(path, "wb");
+    if (!f) return ZKW_ERR_INVALID;
+    int rc = write_vk_part(f, pk, kPkMagic);
+    const size_t vb = pk->n * 32;
+    std::vector<uint8_t> host(vb);
+    auto dump = [&](const uint64_t* dev) -> int {
+        if (cudaMemcpy(host.data(), dev, vb, cudaMemcpyDeviceToHost) != cudaSuccess) return ZKW_ERR_CUDA;
+        return fwrite(host.data(), 1, vb, f) == vb ? ZKW_OK : ZKW_ERR_INVALID;
+    };
+    for (unsigned c = 0; c < pk->nfixed && rc == ZKW_OK; c++) { rc = dump(pk->fixed_values[c]); if (rc == ZKW_OK) rc = dump(pk->fixed_polys[c]); }
+    for (unsigned c = 0; c < pk->nperm && rc == ZKW_OK; c++) { rc = dump(pk->sigma_values[c]); if (rc == ZKW_OK) rc = dump(pk->sigma_polys[c]); }
+    if (fclose(f) != 0 && rc == ZKW_OK) rc = ZKW_ERR_INVALID;
+    return rc;
+}
+
+int zkw_pk_read(zkw_ctx* ctx, const char* path, zkw_pk** out) {
+    if (!ctx || !path || !out) return ZKW_ERR_INVALID;
+    *out = nullptr;
+    ZKW_CUDA(ctx, cudaSetDevice(ctx->device));
+    FILE* f = fopen(path, "rb");
+    if (!f) return ZKW_ERR_INVALID;
+    std::unique_ptr<FILE, int (*)(FILE*)> closer(f, fclose);
+    char magic[8];
+    zkw_circuit_shape sh;
+    uint32_t counts[2];
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, kPkMagic, 8) || fread(&sh, sizeof sh, 1, f) != 1 || fread(counts, 4, 2, f) != 2) return ZKW_ERR_INVALID;
+    if (sh.k < 4 || sh.k > 26 || sh.cs_degree < 4 || sh.cs_degree > 5 || sh.num_advice == 0 || sh.num_fixed == 0 || sh.ext_k < sh.k || sh.ext_k > sh.k + 2)
+        return ZKW_ERR_INVALID;
+    if (!ctx->bases[ZKW_BASES_G].points || ctx->bases[ZKW_BASES_G].n != ((size_t)1 << sh.k)) return ZKW_ERR_STATE;
+    std::unique_ptr<zkw_pk, void (*)(zkw_pk*)> pk(new zkw_pk(), [](zkw_pk* p) { for (void* q : p->owned) cudaFree(q); delete p; });
+    pk->shape = sh;
+    pk->n = (size_t)1 << sh.k; pk->en = (size_t)1 << sh.ext_k;
+    pk->u = pk->n - (sh.blinding_factors + 1);
+    pk->A = sh.num_advice; pk->L = sh.num_lookup_advice; pk->F = sh.num_fixed;
+    pk->nfixed = pk->F + 1 + pk->A + (pk->L == 0 ? 1 : 0);
+    pk->nperm = pk->F + pk->A + pk->L;
+    pk->chunk = sh.cs_degree - 2;
+    pk->nsets = (pk->nperm + pk->chunk - 1) / pk->chunk;
+    pk->nlk = pk->L ? pk->L : 1;
+    if (counts[0] != pk->nfixed || counts[1] != pk->nperm || pk->chunk > 8) return ZKW_ERR_INVALID;
+    if (fread(pk->digest, 8, 4, f) != 4) return ZKW_ERR_INVALID;
+    pk->fixed_commitments.resize(pk->nfixed); pk->perm_commitments.resize(pk->nperm);
+    for (auto& c : pk->fixed_commitments) if (fread(c.data(), 8, 8, f) != 8) return ZKW_ERR_INVALID;
+    for (auto& c : pk->perm_commitments) if (fread(c.data(), 8, 8, f) != 8) return ZKW_ERR_INVALID;
+    const size_t n = pk->n, vb = n * 32, eb = pk->en * 32;
+    Domain dom;
+    ZKW_TRY(make_domain(ctx, sh, &dom));
+    cudaStream_t st = ctx->stream;
+    std::vector<uint64_t> host(4 * n), table_host;
+    auto load = [&](uint64_t** dev, bool keep_table) -> int {
+        if (fread(host.data(), 1, vb, f) != vb) return ZKW_ERR_INVALID;
+        if (keep_table) table_host = host;
+        ZKW_TRY(dmalloc(ctx, pk.get(), vb, (void**)dev));
+        ZKW_CUDA(ctx, cudaMemcpyAsync(*dev, host.data(), vb, cudaMemcpyHostToDevice, st));
+        ZKW_CUDA(ctx, cudaStreamSynchronize(st));     // `host` is reused by the next column
+        return ZKW_OK;
+    };
+    auto coset_of = [&](const uint64_t* poly, uint64_t** coset) -> int {
+        ZKW_TRY(dmalloc(ctx, pk.get(), eb, (void**)coset));
+        return ntt_run(ctx, poly, sh.k, *coset, sh.ext_k, dom.dc.ext_omega, true, nullptr);
+    };
+    pk->fixed_values.resize(pk->nfixed); pk->fixed_polys.resize(pk->nfixed); pk->fixed_cosets.resize(pk->nfixed);
+    for (unsigned c = 0; c < pk->nfixed; c++) {
+        ZKW_TRY(load(&pk->fixed_values[c], c == pk->table_col()));
+        ZKW_TRY(load(&pk->fixed_polys[c], false));
+        ZKW_TRY(coset_of(pk->fixed_polys[c], &pk->fixed_cosets[c]));
+    }
+    pk->sigma_values.resize(pk->nperm); pk->sigma_polys.resize(pk->nperm); pk->sigma_cosets.resize(pk->nperm);
+    for (unsigned c = 0; c < pk->nperm; c++) {
+        ZKW_TRY(load(&pk->sigma_values[c], false));
+        ZKW_TRY(load(&pk->sigma_polys[c], false));
+        ZKW_TRY(coset_of(pk->sigma_polys[c], &pk->sigma_cosets[c]));
+    }
+    ZKW_TRY(pk_derived(ctx, pk.get(), dom, table_host.data()));
+    ZKW_CUDA(ctx, cudaStreamSynchronize(st));
+    *out = pk.release();
     return ZKW_OK;
 }
 

@@ -29,6 +29,7 @@ ZKW_ERR_INVALID = -3
 ZKW_ERR_OOM = -4
 ZKW_ERR_STATE = -5
 ZKW_ERR_UNSUPPORTED = -6
+ZKW_ERR_SIGNATURE = -7
 
 BASES_G, BASES_G_LAGRANGE, BASES_CALLER = 0, 1, 2
 
@@ -48,6 +49,9 @@ EXPORTS = [
     "zkw_synth_witness", "zkw_host_alloc", "zkw_host_free",
     "zkw_ecdsa_circuit_new", "zkw_ecdsa_circuit_free", "zkw_ecdsa_circuit_shape", "zkw_ecdsa_circuit_rows", "zkw_ecdsa_circuit_fixed",
     "zkw_ecdsa_circuit_permutation", "zkw_ecdsa_synthesize",
+    "zkw_pk_write", "zkw_pk_read", "zkw_vk_write", "zkw_vk_read",
+    "zkw_prover_create", "zkw_prover_destroy", "zkw_prover_ctx", "zkw_prover_pk", "zkw_prover_last_synthesis_ms", "zkw_prover_prove",
+    "zkw_prove_batch",
 ]
 
 
@@ -143,6 +147,22 @@ def load_library() -> C.CDLL:
     lib.zkw_ecdsa_circuit_fixed.argtypes = [C.c_void_p, C.POINTER(u64p)]
     lib.zkw_ecdsa_circuit_permutation.argtypes = [C.c_void_p, C.POINTER(u32p)]
     lib.zkw_ecdsa_synthesize.argtypes = [C.c_void_p, u8p, u8p, u8p, u8p, u8p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    lib.zkw_pk_write.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+    lib.zkw_pk_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.zkw_vk_write.argtypes = [C.c_void_p, C.c_char_p]
+    lib.zkw_vk_read.argtypes = [C.c_char_p, C.POINTER(CircuitShape), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), u64p, C.c_size_t, u64p, C.c_size_t, u64p]
+    lib.zkw_prover_create.argtypes = [C.c_int, C.POINTER(CircuitParamsC), u64p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.zkw_prover_destroy.argtypes = [C.c_void_p]
+    lib.zkw_prover_destroy.restype = None
+    lib.zkw_prover_ctx.argtypes = [C.c_void_p]
+    lib.zkw_prover_ctx.restype = C.c_void_p
+    lib.zkw_prover_pk.argtypes = [C.c_void_p]
+    lib.zkw_prover_pk.restype = C.c_void_p
+    lib.zkw_prover_last_synthesis_ms.argtypes = [C.c_void_p]
+    lib.zkw_prover_last_synthesis_ms.restype = C.c_double
+    lib.zkw_prover_prove.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_uint, C.POINTER(C.c_uint8), C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.zkw_prove_batch.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_int, C.c_uint, C.POINTER(C.c_uint8),
+                                    C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
     _lib = lib
     return lib
 
@@ -199,22 +219,27 @@ def _addr(x) -> C.c_void_p:
 class Context:
     """One zkw_ctx: bound to one CUDA device, one stream.  One Context per GPU / per process."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed=None):
         self.lib = load_library()
+        self.device = device
+        self._host_allocs: list = []
+        self._owned = _borrowed is None
+        if _borrowed is not None:          # a context owned by a zkw_prover
+            self.h = C.c_void_p(_borrowed)
+            return
         h = C.c_void_p()
         rc = self.lib.zkw_ctx_create(device, C.byref(h))
         if rc != ZKW_OK:
             raise ZkwError(rc, "zkw_ctx_create")
         self.h = h
-        self.device = device
-        self._host_allocs: list = []
 
     def close(self):
         if getattr(self, "h", None):
             for p in self._host_allocs:
                 self.lib.zkw_host_free(self.h, p)
             self._host_allocs = []
-            self.lib.zkw_ctx_destroy(self.h)
+            if self._owned:
+                self.lib.zkw_ctx_destroy(self.h)
             self.h = None
 
     def __del__(self):  # pragma: no cover
