@@ -377,6 +377,59 @@ def host_threads() -> int:
         return max(1, os.cpu_count() or 1)
 
 
+def split_msm_leg(zkw, torch, dist, rank, world, local, ks=(20, 22), reps=7):
+    """One 2^k-point MSM over `world` GPUs: rank r holds slice r of the basis (2^k / world points tau_r^i G with their window
+    tables), the scalars are already on each device.  Timed on the host around device MSM + NCCL all-gather + host fold,
+    max over ranks, median of `reps`."""
+    mg = importlib.import_module("webauthn-halo2_b200.multi_gpu")
+    dev = torch.device("cuda", local)
+    rows = []
+    for k in ks:
+        n = 1 << k
+        if n % world:
+            continue
+        m = n // world
+        ctx = zkw.Context(local)
+        tau = np.array([0x1234567890ABCDEF + rank, 0x0FEDCBA987654321, 0x1111111111111111, 0x0222222222222222], dtype=np.uint64)
+        ctx.srs_setup(m.bit_length() - 1, tau)                       # this rank's slice, with window tables
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1000 + k)                                    # the same scalar vector on every rank
+        s = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device=dev, generator=gen)
+        s[:, 3] &= (1 << 60) - 1
+        mine = s[rank * m:(rank + 1) * m].contiguous()
+
+        def once():
+            part = ctx.msm_dev(mine, m, zkw.BASES_G)
+            return mg._gather_and_fold(part, world, dist, dev)
+
+        res = once()
+        ts = []
+        for _ in range(reps):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = once()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            ts.append(float(dt.item()) * 1e3)
+        ts.sort()
+        # check: rank 0 gathers every slice of the basis and computes the whole MSM alone (caller bases)
+        g_mine = torch.from_numpy(ctx.srs_get(zkw.BASES_G, m).view(np.int64)).to(dev)
+        g_all = [torch.empty_like(g_mine) for _ in range(world)]
+        dist.all_gather(g_all, g_mine)
+        ok = None
+        if rank == 0:
+            whole = ctx.msm_dev(s, n, zkw.BASES_CALLER, bases_dev=torch.cat(g_all))
+            ok = bool(np.array_equal(whole, res))
+        rows.append({"k": k, "points": n, "gpus": world, "ms": ts[len(ts) // 2], "points_per_s": n / ts[len(ts) // 2] * 1e3,
+                     "matches_single_gpu_msm": ok})
+        ctx.close()
+        del s, mine, g_all, g_mine
+        torch.cuda.empty_cache()
+    return {"rows": rows, "path": "multi_gpu._gather_and_fold: per-rank zkw_msm_bn254_g1_dev over resident window tables, NCCL all-gather of "
+                                  "world x 96 bytes, host fold (zkw_g1_sum)"}
+
+
 def config_dict(args, workload: str) -> dict:
     """Identical in both arms (the driver compares them)."""
     return {"workload": workload, "k": args.k, "proofs_per_step_per_gpu": 1,
@@ -590,6 +643,13 @@ def run_b200(args):
                  "all_proofs_distinct": len(set(proofs)) == len(proofs)}
         pool.close()
 
+    # BASELINE configs[4], multi-GPU leg: ONE MSM of 2^20 / 2^22 points split over the ranks (each rank keeps the window
+    # tables of its slice resident; NCCL all-gather of the 96-byte partial results; host fold), checked against the same
+    # MSM computed by rank 0 alone
+    split = None
+    if world > 1 and args.split_msm and args.workload != "hotpath":
+        split = split_msm_leg(zkw, torch, dist, rank, world, local)
+
     if rank == 0:
         pk, pk_src = peaks()
         n = 1 << args.k
@@ -634,7 +694,7 @@ def run_b200(args):
             "circuit": state.state.circuit.stats() if args.workload != "hotpath" else None,
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample},
-            "e2e": e2e, "batch": batch, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+            "e2e": e2e, "batch": batch, "split_msm": split, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
             "published_reference": {"value": 1.0 / 14.846241542, "unit": UNIT, "hardware": "M1 Pro (halo2-circuits/src/results/ecdsa_bench.csv:2)",
                                     "note": "full create_proof incl. halo2-ecc witness synthesis, Blake2b + SHPLONK; not the same hardware or witness"},
         }
@@ -657,6 +717,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-flavours", dest="flavours", action="store_false", help="skip the Blake2b/SHPLONK and k = 17 timings")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-split-msm", dest="split_msm", action="store_false", help="N > 1: skip the single-MSM-split-over-ranks leg")
     ap.add_argument("--no-three-seam", dest="three_seam", action="store_false", help="skip the host-pointer three-seam figure")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the

@@ -113,6 +113,10 @@ int zkw_msm_bn254_g1_dev_to_host(zkw_ctx* ctx, int which_bases, const uint64_t* 
 /* Jacobian -> affine (x,y) Montgomery, (0,0) for the identity: C::Curve::batch_normalize. */
 int zkw_g1_batch_normalize(zkw_ctx* ctx, const uint64_t* xyz /* m*12 */, size_t m, uint64_t* out_xy /* m*8 */);
 
+/* Sum of m Jacobian points on the HOST, normalised to (x, y, 1) (identity: z = 0): folds the per-GPU partial results of
+ * one MSM split across GPUs (each rank's zkw_msm_* result, all-gathered: 96 bytes per rank). */
+int zkw_g1_sum(const uint64_t* xyz /* m*12 */, size_t m, uint64_t out_xyz[12]);
+
 /* ---- NTT: halo2_proofs::arithmetic::best_fft(a, omega, log_n) ------------------------------ */
 /* In place, natural order in and out: a[i] <- sum_j a[j] * omega^(i*j).  scale_or_null, if
  * given, multiplies every output (n^-1 for an inverse transform). */

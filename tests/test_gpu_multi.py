@@ -42,6 +42,13 @@ def _worker(rank, world, port, n, q):
     out = mg.split_msm(ctx, s, b, rank, world, dist, device=torch.device("cuda", rank))
     want = cpu.g1_to_affine(cpu.best_multiexp(s, b, 2))[0]
     ok_msm = bool(np.array_equal(out[:8], want))
+    # the resident form: this rank's slice of the basis (with window tables) stays in HBM, scalars are on the device
+    lo, hi = mg.shard_range(n, rank, world)
+    sctx = zkw.Context(rank)
+    sm = mg.SplitMsm(sctx, b[lo:hi], n, rank, world, dist, device=torch.device("cuda", rank))
+    s_dev = torch.from_numpy(s[lo:hi].view(np.int64)).to(torch.device("cuda", rank))
+    ok_msm = ok_msm and bool(np.array_equal(sm(s_dev)[:8], want))
+    sctx.close()
     # independent proofs, sharded round-robin: each rank proves its share on its own GPU
     st = zkw.ProverState(zkw.CircuitParams("Simple", 10, 2, 1, 1, 8, 88, 3), rank, synthetic=True)
     mine = mg.shard_indices(6, rank, world)

@@ -505,6 +505,35 @@ static void msm_host_tail(const uint32_t* s_xyzz /* [G][c][32] */, int groups, i
     memcpy(out_xyz + 8, z.l, 32);
 }
 
+}  // namespace zkw
+
+// Sum of m Jacobian points (x, y, z Montgomery; z = 0 is the identity) on the HOST, normalised to (x, y, 1): the fold of
+// the per-GPU partial results of a split MSM - m - 1 point additions and one inversion, microseconds.
+extern "C" int zkw_g1_sum(const uint64_t* xyz, size_t m, uint64_t out_xyz[12]) {
+    using namespace zkw;
+    if ((!xyz && m) || !out_xyz) return ZKW_ERR_INVALID;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (size_t i = 0; i < m; i++) {
+        Fq x, y, z;
+        memcpy(x.l, xyz + 12 * i, 32); memcpy(y.l, xyz + 12 * i + 4, 32); memcpy(z.l, xyz + 12 * i + 8, 32);
+        if (z.is_zero()) continue;
+        G1Xyzz p;
+        p.x = x; p.y = y; p.zz = z * z; p.zzz = p.zz * z;
+        acc.add(p);
+    }
+    Fq x = Fq::zero(), y = Fq::one(), z = Fq::zero();
+    if (!acc.is_identity()) {
+        Fq tinv = fp_inv_bingcd(acc.zz * acc.zzz);
+        x = acc.x * (acc.zzz * tinv);
+        y = acc.y * (acc.zz * tinv);
+        z = Fq::one();
+    }
+    memcpy(out_xyz, x.l, 32); memcpy(out_xyz + 4, y.l, 32); memcpy(out_xyz + 8, z.l, 32);
+    return ZKW_OK;
+}
+
+namespace zkw {
+
 static int lane_init(zkw_ctx* ctx, int lane) {
     if (!ctx->fork_event) ZKW_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     if (lane == 0) { ctx->lane_stream[0] = ctx->stream; }

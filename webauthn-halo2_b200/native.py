@@ -51,7 +51,7 @@ EXPORTS = [
     "zkw_ecdsa_circuit_permutation", "zkw_ecdsa_synthesize",
     "zkw_pk_write", "zkw_pk_read", "zkw_vk_write", "zkw_vk_read",
     "zkw_prover_create", "zkw_prover_destroy", "zkw_prover_ctx", "zkw_prover_pk", "zkw_prover_last_synthesis_ms", "zkw_prover_prove",
-    "zkw_prove_batch",
+    "zkw_prove_batch", "zkw_g1_sum",
 ]
 
 
@@ -147,6 +147,7 @@ def load_library() -> C.CDLL:
     lib.zkw_ecdsa_circuit_fixed.argtypes = [C.c_void_p, C.POINTER(u64p)]
     lib.zkw_ecdsa_circuit_permutation.argtypes = [C.c_void_p, C.POINTER(u32p)]
     lib.zkw_ecdsa_synthesize.argtypes = [C.c_void_p, u8p, u8p, u8p, u8p, u8p, C.POINTER(u64p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    lib.zkw_g1_sum.argtypes = [u64p, C.c_size_t, u64p]
     lib.zkw_pk_write.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
     lib.zkw_pk_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.zkw_vk_write.argtypes = [C.c_void_p, C.c_char_p]
@@ -186,6 +187,16 @@ def synth_witness(shape: "CircuitShape", lookup_bits: int, assertion: bytes, out
     status = lib.zkw_synth_witness(C.byref(shape), C.c_uint32(lookup_bits), assertion, C.c_size_t(len(assertion)), ptrs, None)
     if status != ZKW_OK:
         raise ZkwError(status, "zkw_synth_witness")
+    return out
+
+
+def g1_sum(points_xyz: np.ndarray) -> np.ndarray:
+    """zkw_g1_sum: (m, 12) Jacobian points -> their sum as (x, y, 1), or z = 0 for the identity.  Host code."""
+    pts = _as_u64(points_xyz, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    rc = load_library().zkw_g1_sum(_p(pts), C.c_size_t(pts.shape[0]), _p(out))
+    if rc != ZKW_OK:
+        raise ZkwError(rc, "zkw_g1_sum")
     return out
 
 
