@@ -517,8 +517,18 @@ def synthesize(params: Params, pubkey, r: int, s: int, msghash: int) -> Builder:
     for _ in range(15):
         table.append(b.ec_add(table[-1], pk))
     tx, ty = [t[0] for t in table], [t[1] for t in table]
+    # everything the two window loops consume is laid out before them (the product synthesises the loops' windows on
+    # several host threads, each starting from a recorded row offset): window indicators of both scalars and the
+    # fixed-base accumulator's constant start point -(c*B2), which cancels the variable part's offset in the final addition
+    var_windows = b.scalar_windows(u2)
+    fix_windows = b.scalar_windows(u1)
+    key = params.limb_bits
+    if key not in _FIXED_CACHE:
+        _FIXED_CACHE[key] = (fixed_tables(key), ec_neg(ec_mul(OFFSET_VAR, var_offset_scalar(key))))
+    tabs, start = _FIXED_CACHE[key]
+    facc = (b.const_elem(start[0]), b.const_elem(start[1]))
     acc = None
-    for ind in b.scalar_windows(u2):
+    for ind in var_windows:
         sel = (b.select_elem(ind, tx, False), b.select_elem(ind, ty, False))
         if acc is None:
             acc = sel
@@ -526,14 +536,8 @@ def synthesize(params: Params, pubkey, r: int, s: int, msghash: int) -> Builder:
             for _ in range(WINDOW):
                 acc = b.ec_double(acc)
             acc = b.ec_add(acc, sel)
-    # fixed base: start from -(c*B2) so that the variable part's offset cancels in the final addition
-    key = params.limb_bits
-    if key not in _FIXED_CACHE:
-        _FIXED_CACHE[key] = (fixed_tables(key), ec_neg(ec_mul(OFFSET_VAR, var_offset_scalar(key))))
-    tabs, start = _FIXED_CACHE[key]
-    facc = (b.const_elem(start[0]), b.const_elem(start[1]))
     W = len(tabs)
-    for wi, ind in enumerate(b.scalar_windows(u1)):
+    for wi, ind in enumerate(fix_windows):
         w = W - 1 - wi
         sel = (b.select_elem(ind, [t[0] for t in tabs[w]], True), b.select_elem(ind, [t[1] for t in tabs[w]], True))
         facc = b.ec_add(facc, sel)

@@ -103,6 +103,32 @@ def test_product_synthesis_matches_oracle_cell_for_cell(zkw, k):
         c.close()
 
 
+@pytest.mark.parametrize("k", [19, 16])
+def test_threaded_synthesis_is_identical(zkw, monkeypatch, k):
+    """zkw_ecdsa_synthesize splits the window loops over worker threads that start from recorded row offsets and from the
+    accumulator values of a projective pre-pass: any thread count writes exactly the same cells."""
+    c = zkw.EcdsaCircuit(zkw.CircuitParams.for_degree(k))
+    try:
+        ab = signed_assertion(70 + k)
+        args = [ab["pubkey_x"], ab["pubkey_y"], ab["r"], ab["s"], ab["msg_hash"]]
+        monkeypatch.setenv("ZKW_SYNTH_THREADS", "1")
+        want = c.synthesize(*args)
+        for threads in ("2", "3", "5", "16"):
+            monkeypatch.setenv("ZKW_SYNTH_THREADS", threads)
+            got = c.synthesize(*args)
+            assert all(np.array_equal(a, b) for a, b in zip(got, want)), threads
+        bad = list(args)
+        bad[4] = bytes([bad[4][0] ^ 1]) + bad[4][1:]
+        monkeypatch.setenv("ZKW_SYNTH_THREADS", "1")
+        want_bad = c.synthesize(*bad, allow_invalid=True)
+        monkeypatch.setenv("ZKW_SYNTH_THREADS", "4")
+        with pytest.raises(zkw.InvalidSignature):
+            c.synthesize(*bad)
+        assert all(np.array_equal(a, b) for a, b in zip(c.synthesize(*bad, allow_invalid=True), want_bad))
+    finally:
+        c.close()
+
+
 def test_product_refuses_invalid_signatures(zkw):
     c = zkw.EcdsaCircuit(zkw.CircuitParams.for_degree(17))
     try:

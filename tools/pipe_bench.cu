@@ -1,6 +1,10 @@
 // pipe_bench.cu — issue rates of the integer / fp64 instructions a 254-bit Montgomery product can be
 // built from, in lane-operations per clock per SM (development aid; explains the ALU ceiling in DESIGN.md).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe tools/pipe_bench.cu && /tmp/pipe
+// Every multiply takes a LOOP-VARIANT operand (the low word of the neighbouring chain's accumulator), otherwise
+// ptxas hoists the product out of the loop and the "multiply" test times additions (the round-1 version did exactly
+// that for the plain mad.wide line).  tools/pipe_bench_sass.sh dumps the loop bodies' SASS so that the mnemonic each
+// line really measures is on record (profiles/r2_pipe_sass.txt).
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -18,25 +22,26 @@ __global__ void k(uint32_t* out, uint32_t seed) {
     double d[U];
     double da = 1.0 + (double)(threadIdx.x & 7) * 1e-9, db = 1.0 - 1e-9;
 #pragma unroll
-    for (int j = 0; j < U; j++) { w[j] = j + seed; lo[j] = j + a; hi[j] = j ^ b; d[j] = (double)j; }
+    for (int j = 0; j < U; j++) { w[j] = j + seed + ((uint64_t)a << 7); lo[j] = j + a; hi[j] = j ^ b ^ a; d[j] = (double)j; }   // thread-variant: keeps the work off the uniform datapath
     for (int i = 0; i < ITERS; i++) {
 #pragma unroll
         for (int j = 0; j < U; j++) {
-            if (OP == MAD_WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a), "r"(b));
+            const uint32_t va = (uint32_t)w[(j + 1) % U], vl = lo[(j + 1) % U];   // loop-variant multiplicands
+            if (OP == MAD_WIDE) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(va), "r"(b));
             if (OP == MAD_LOHI_CC)
-                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
-            if (OP == MAD_LO) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
-            if (OP == MAD_HI) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(vl), "r"(b));
+            if (OP == MAD_LO) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(vl), "r"(b));
+            if (OP == MAD_HI) asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(vl), "r"(b));
             if (OP == DFMA) asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[j]) : "d"(da), "d"(db));
             if (OP == IADD3_CC) asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
             if (OP == LOP3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(lo[j]) : "r"(a), "r"(hi[j]));
             if (OP == MAD_WIDE_PLUS_ALU) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(va), "r"(b));
                 asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
             }
             if (OP == DFMA_PLUS_MADWIDE) {
                 asm volatile("fma.rz.f64 %0, %1, %2, %0;" : "+d"(d[j]) : "d"(da), "d"(db));
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a), "r"(b));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(va), "r"(b));
             }
         }
     }
@@ -49,7 +54,7 @@ __global__ void k(uint32_t* out, uint32_t seed) {
                              "madc.lo.cc.u32 %4, %8, %9, %4;\n\tmadc.hi.cc.u32 %5, %8, %9, %5;\n\t"
                              "madc.lo.cc.u32 %6, %8, %9, %6;\n\tmadc.hi.u32 %7, %8, %9, %7;"
                              : "+r"(lo[j]), "+r"(hi[j]), "+r"(lo[j + 1]), "+r"(hi[j + 1]), "+r"(lo[j + 2]), "+r"(hi[j + 2]), "+r"(lo[j + 3]), "+r"(hi[j + 3])
-                             : "r"(a), "r"(b));
+                             : "r"(lo[(j + 4) % U]), "r"(b));
         }
     }
     uint32_t acc = 0;

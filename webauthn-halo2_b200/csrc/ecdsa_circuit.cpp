@@ -25,6 +25,8 @@
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 #include "../../include/zkw_b200.h"
@@ -277,6 +279,7 @@ struct Elem {
     uint32_t native;
     U256 value;     // canonical integer < 2^256
     u128 lv[3];
+    U256 nat;       // value of the native cell (value mod r)
 };
 struct Term {
     const Elem* X;
@@ -305,6 +308,14 @@ struct Structure {   // what keygen needs; filled by the structure pass
     std::vector<U256> constants;
     std::vector<uint32_t> lookups;
     std::vector<uint64_t> rows;          // cells used per advice column (gate.., lookup..)
+    // segment s >= 1 of run() (variable-base windows 1.., fixed-base windows 0.., final addition) starts with these
+    // per-column row counters and these accumulator cells: what a worker thread needs to synthesise it independently
+    struct Checkpoint {
+        std::vector<uint64_t> rows;
+        uint32_t acc_ids[8], facc_ids[8];   // x limbs 0-2, x native, y limbs 0-2, y native
+        uint64_t cells_before;
+    };
+    std::vector<Checkpoint> checkpoints;
 };
 
 struct Builder {
@@ -449,6 +460,20 @@ struct Builder {
         c_last = put_w(c_acc);
         gate(3 * c_terms++);
     }
+    inline void cterm_vv(uint32_t a, const U256& av, uint32_t b, const U256& bv) {   // operands whose values the caller holds
+        c_acc = muladd(c_acc, av, bv);
+        put_xv(a, av);
+        put_xv(b, bv);
+        c_last = put_w(c_acc);
+        gate(3 * c_terms++);
+    }
+    inline void cterm_vc(uint32_t a, const U256& av, const U256& cst) {
+        c_acc = muladd(c_acc, av, cst);
+        put_xv(a, av);
+        put_c(cst);
+        c_last = put_w(c_acc);
+        gate(3 * c_terms++);
+    }
     inline void cterm_xc(uint32_t a, const U256& cst) {
         const U256 av = val(a);
         c_acc = muladd(c_acc, av, cst);
@@ -534,6 +559,7 @@ struct Builder {
             e.limbs[i] = range_limbs(v, bits[i]);
         }
         e.native = native_of(e.limbs);
+        e.nat = c_acc;
         return e;
     }
     Elem const_elem(const U256& value) {
@@ -542,7 +568,8 @@ struct Builder {
         split(value, e.lv);
         begin();
         for (int i = 0; i < 3; i++) e.limbs[i] = put(ic(from128(e.lv[i])));
-        e.native = put(ic(moduli().fr.reduce(value)));
+        e.nat = moduli().fr.reduce(value);
+        e.native = put(ic(e.nat));
         end();
         return e;
     }
@@ -657,6 +684,7 @@ struct Builder {
             const unsigned bits[3] = {LB, LB, q_top_bits};
             for (int i = 0; i < 3; i++) qe.limbs[i] = range_limbs(qe.lv[i], bits[i]);
             qe.native = native_of(qe.limbs);
+            qe.nat = c_acc;
         }
         // constant limbs: (k+ + 2^258 m) mod 2^(3 LB), k-
         uint64_t K9[9];
@@ -715,19 +743,22 @@ struct Builder {
         uint32_t rend = cend();
         equal(lend, rend);
     }
+    // operand values come from the Elems, never from the cells: an accumulator handed over from another worker thread's
+    // segment may not have been written yet
     void limb_terms(const Term* ts, unsigned nt, unsigned i) {
         for (unsigned t = 0; t < nt; t++) {
             if (ts[t].Y) {
-                for (unsigned j = 0; j <= i; j++) cterm_xx(ts[t].X->limbs[j], ts[t].Y->limbs[i - j]);
+                for (unsigned j = 0; j <= i; j++)
+                    cterm_vv(ts[t].X->limbs[j], from128(ts[t].X->lv[j]), ts[t].Y->limbs[i - j], from128(ts[t].Y->lv[i - j]));
             } else {
-                cterm_xc(ts[t].X->limbs[i], u256(ts[t].scalar));
+                cterm_vc(ts[t].X->limbs[i], from128(ts[t].X->lv[i]), u256(ts[t].scalar));
             }
         }
     }
     void nat_terms(const Term* ts, unsigned nt) {
         for (unsigned t = 0; t < nt; t++) {
-            if (ts[t].Y) cterm_xx(ts[t].X->native, ts[t].Y->native);
-            else cterm_xc(ts[t].X->native, u256(ts[t].scalar));
+            if (ts[t].Y) cterm_vv(ts[t].X->native, ts[t].X->nat, ts[t].Y->native, ts[t].Y->nat);
+            else cterm_vc(ts[t].X->native, ts[t].X->nat, u256(ts[t].scalar));
         }
     }
     void constrain(const ModConst& mc, std::initializer_list<Term> pos, std::initializer_list<Term> neg, const U256& kpos = u256(0),
@@ -891,6 +922,7 @@ struct Builder {
             e.limbs[i] = cend();
         }
         e.native = native_of(e.limbs);
+        e.nat = c_acc;
         e.value = consts ? consts[sel] : table[sel]->value;
         split(e.value, e.lv);
         return e;
@@ -902,6 +934,9 @@ struct Builder {
     // inversion over a projective pre-pass (precompute_denominators); empty = invert one by one
     std::vector<U256> dinv_queue;
     size_t dinv_next = 0;
+    // affine coordinates (canonical) of the variable-base accumulator after window wi and of the fixed-base accumulator
+    // after window wi, from the same pre-pass: lets a worker thread start in the middle of run()
+    std::vector<U256> traj_acc_x, traj_acc_y, traj_facc_x, traj_facc_y;
     U256 denominator_inverse(const U256& d) {
         if (dinv_next < dinv_queue.size()) {
             const U256& c = dinv_queue[dinv_next++];
@@ -1074,16 +1109,20 @@ struct Builder {
         table[0] = affine(OFF_VAR_X, OFF_VAR_Y);
         for (unsigned j = 1; j < 16; j++)
             if ((table[j] = add(table[j - 1], pk)) < 0) return false;
+        std::vector<int> acc_at(nw), facc_at(nw);
         int acc = table[d2[0]];
+        acc_at[0] = acc;
         for (unsigned wi = 1; wi < nw; wi++) {
             for (unsigned i = 0; i < WINDOW; i++) acc = dbl(acc);
             if ((acc = add(acc, table[d2[wi]])) < 0) return false;
+            acc_at[wi] = acc;
         }
         int facc = affine(tabs->start_x, tabs->start_y);
         for (unsigned wi = 0; wi < nw; wi++) {
             unsigned w = nw - 1 - wi;
             int t = affine(tabs->x[16 * w + d1[wi]], tabs->y[16 * w + d1[wi]]);
             if ((facc = add(facc, t)) < 0) return false;
+            facc_at[wi] = facc;
         }
         if (add(acc, facc) < 0) return false;
         // affine coordinates of every point: x = X / Z^2, y = Y / Z^3
@@ -1107,11 +1146,27 @@ struct Builder {
         batch_invert(f, den);
         dinv_queue.resize(ops.size());
         for (size_t i = 0; i < ops.size(); i++) dinv_queue[i] = f.from(den[i]);
+        traj_acc_x.resize(nw); traj_acc_y.resize(nw); traj_facc_x.resize(nw); traj_facc_y.resize(nw);
+        for (unsigned wi = 0; wi < nw; wi++) {
+            traj_acc_x[wi] = f.from(ax[acc_at[wi]]); traj_acc_y[wi] = f.from(ay[acc_at[wi]]);
+            traj_facc_x[wi] = f.from(ax[facc_at[wi]]); traj_facc_y[wi] = f.from(ay[facc_at[wi]]);
+        }
         return true;
     }
 
     // ---- the circuit (mirrors oracle/ecdsa_circuit.py: synthesize) -------------------------------------------------
-    void run(const U256& pkx, const U256& pky, const U256& r, const U256& s, const U256& msghash, bool* sig_ok) {
+    // Everything the window loops read but do not write: produced by the prologue, shared (read-only) by the workers.
+    struct RunCtx {
+        std::vector<EPt> table;
+        std::vector<uint32_t> inds_var, inds_fix;
+        Elem r_e;
+        U256 r, s;
+        unsigned nw = 0;
+    };
+    unsigned num_segments(unsigned nw) const { return 2 * nw + 1; }   // 0 prologue | 1..nw-1 variable | nw..2nw-1 fixed | 2nw final
+
+    // ecdsa_p256.rs:139-177 (load m, r, s, the public key) through the first variable-base window
+    void prologue(const U256& pkx, const U256& pky, const U256& r, const U256& s, const U256& msghash, RunCtx& rc, EPt& acc, EPt& facc) {
         Elem m_e = new_elem(msghash), r_e = new_elem(r), s_e = new_elem(s);
         EPt pk{new_elem(pkx), new_elem(pky)};
         assert_on_curve(pk);
@@ -1123,50 +1178,95 @@ struct Builder {
         Elem u2 = divide(r_e, s_e, mc_n);
         assert_less_than(u1, P256_N);
         assert_less_than(u2, P256_N);
-        // variable base
-        std::vector<EPt> table(16);
-        table[0] = EPt{const_elem(OFF_VAR_X), const_elem(OFF_VAR_Y)};
-        for (unsigned j = 1; j < 16; j++) table[j] = ec_add(table[j - 1], pk);
+        rc.r_e = r_e;
+        rc.r = r;
+        rc.s = s;
+        // variable base: table T[d] = d * PK + B2
+        rc.table.resize(16);
+        rc.table[0] = EPt{const_elem(OFF_VAR_X), const_elem(OFF_VAR_Y)};
+        for (unsigned j = 1; j < 16; j++) rc.table[j] = ec_add(rc.table[j - 1], pk);
+        // window indicators of both scalars and the fixed-base start point, then the first window: acc = T[top digit]
+        scalar_windows(u2, rc.inds_var);
+        scalar_windows(u1, rc.inds_fix);
+        rc.nw = (unsigned)rc.inds_var.size() / 16;
+        facc = EPt{const_elem(tabs->start_x), const_elem(tabs->start_y)};
+        acc = select_point(rc, 0);
+    }
+    EPt select_point(const RunCtx& rc, unsigned wi) {
         const Elem* tx[16];
         const Elem* ty[16];
         for (unsigned j = 0; j < 16; j++) {
-            tx[j] = &table[j].x;
-            ty[j] = &table[j].y;
+            tx[j] = &rc.table[j].x;
+            ty[j] = &rc.table[j].y;
         }
-        std::vector<uint32_t> inds;
-        scalar_windows(u2, inds);
-        const unsigned nw = (unsigned)inds.size() / 16;
-        EPt acc;
-        for (unsigned wi = 0; wi < nw; wi++) {
-            EPt sel;
-            sel.x = select_elem(&inds[16 * wi], tx, nullptr);
-            sel.y = select_elem(&inds[16 * wi], ty, nullptr);
-            if (wi == 0) {
-                acc = sel;
-            } else {
+        EPt sel;
+        sel.x = select_elem(&rc.inds_var[16 * wi], tx, nullptr);
+        sel.y = select_elem(&rc.inds_var[16 * wi], ty, nullptr);
+        return sel;
+    }
+    static void ids_of(const EPt& p, uint32_t ids[8]) {
+        for (int i = 0; i < 3; i++) { ids[i] = p.x.limbs[i]; ids[4 + i] = p.y.limbs[i]; }
+        ids[3] = p.x.native;
+        ids[7] = p.y.native;
+    }
+    Elem elem_at(const uint32_t ids[4], const U256& value) const {
+        Elem e;
+        for (int i = 0; i < 3; i++) e.limbs[i] = ids[i];
+        e.native = ids[3];
+        e.value = value;
+        split(value, e.lv);
+        e.nat = moduli().fr.reduce(value);
+        return e;
+    }
+    // segments [s0, s1) of run(), in order; acc / facc are the accumulators at the start of s0 and at the end of s1 - 1
+    void run_segments(const RunCtx& rc, unsigned s0, unsigned s1, EPt& acc, EPt& facc, bool* sig_ok) {
+        const unsigned nw = rc.nw;
+        for (unsigned sgm = s0; sgm < s1; sgm++) {
+            if (st) {
+                Structure::Checkpoint cp;
+                cp.rows = rows;
+                ids_of(acc, cp.acc_ids);
+                ids_of(facc, cp.facc_ids);
+                cp.cells_before = 0;
+                for (uint64_t r : rows) cp.cells_before += r;
+                if (st->checkpoints.size() <= sgm) st->checkpoints.resize(sgm + 1);
+                st->checkpoints[sgm] = cp;
+            }
+            if (sgm < nw) {                       // variable base: acc = 16 * acc + T[window]
+                EPt sel = select_point(rc, sgm);
                 for (unsigned i = 0; i < WINDOW; i++) acc = ec_double(acc);
                 acc = ec_add(acc, sel);
+            } else if (sgm < 2 * nw) {            // fixed base: facc += Tab[w][window]
+                const unsigned wi = sgm - nw, w = nw - 1 - wi;
+                EPt sel;
+                sel.x = select_elem(&rc.inds_fix[16 * wi], nullptr, &tabs->x[16 * w]);
+                sel.y = select_elem(&rc.inds_fix[16 * wi], nullptr, &tabs->y[16 * w]);
+                facc = ec_add(facc, sel);
+            } else {                              // R = u1*G + u2*PK (strict), R.x == r limb by limb
+                EPt R = ec_add(acc, facc, true);
+                bool ok = true;
+                for (int i = 0; i < 3; i++) {
+                    equal(R.x.limbs[i], rc.r_e.limbs[i]);
+                    ok = ok && R.x.lv[i] == rc.r_e.lv[i];
+                }
+                // r, s in [1, n-1] (the copy constraint above is necessary, not sufficient)
+                ok = ok && !is_zero(rc.r) && !is_zero(rc.s) && cmp(rc.r, P256_N) < 0 && cmp(rc.s, P256_N) < 0;
+                if (sig_ok) *sig_ok = ok;
             }
         }
-        // fixed base
-        EPt facc{const_elem(tabs->start_x), const_elem(tabs->start_y)};
-        scalar_windows(u1, inds);
-        for (unsigned wi = 0; wi < nw; wi++) {
-            unsigned w = nw - 1 - wi;
-            EPt sel;
-            sel.x = select_elem(&inds[16 * wi], nullptr, &tabs->x[16 * w]);
-            sel.y = select_elem(&inds[16 * wi], nullptr, &tabs->y[16 * w]);
-            facc = ec_add(facc, sel);
-        }
-        EPt R = ec_add(acc, facc, true);
-        bool ok = true;
-        for (int i = 0; i < 3; i++) {
-            equal(R.x.limbs[i], r_e.limbs[i]);
-            ok = ok && R.x.lv[i] == r_e.lv[i];
-        }
-        // r, s in [1, n-1] (the copy constraint above is necessary, not sufficient)
-        ok = ok && !is_zero(r) && !is_zero(s) && cmp(r, P256_N) < 0 && cmp(s, P256_N) < 0;
-        if (sig_ok) *sig_ok = ok;
+    }
+    // index into dinv_queue of the first curve operation of segment sgm (15 table additions come first)
+    static size_t first_op_of(unsigned sgm, unsigned nw) {
+        if (sgm < nw) return 15 + (size_t)(sgm - 1) * (WINDOW + 1);
+        const size_t var_ops = 15 + (size_t)(nw - 1) * (WINDOW + 1);
+        return var_ops + (sgm - nw);
+    }
+    // the whole circuit on the calling thread (mirrors oracle/ecdsa_circuit.py: synthesize)
+    void run(const U256& pkx, const U256& pky, const U256& r, const U256& s, const U256& msghash, bool* sig_ok) {
+        RunCtx rc;
+        EPt acc, facc;
+        prologue(pkx, pky, r, s, msghash, rc, acc, facc);
+        run_segments(rc, 1, num_segments(rc.nw), acc, facc, sig_ok);
     }
 };
 
@@ -1203,6 +1303,14 @@ void setup_builder(Builder& b, const zkw_ecdsa_circuit* c) {
     b.P2[256] = u256(0);
     b.init_mod(b.mc_p, moduli().fp);
     b.init_mod(b.mc_n, moduli().fn);
+}
+
+// worker threads of one synthesis: ZKW_SYNTH_THREADS, default min(4, hardware threads / 2)
+unsigned synth_threads() {
+    const char* e = getenv("ZKW_SYNTH_THREADS");
+    if (e && atoi(e) > 0) return (unsigned)std::min(atoi(e), 16);
+    static const unsigned hw = std::thread::hardware_concurrency();
+    return std::max(1u, std::min(4u, hw / 2));
 }
 
 U256 load_le(const uint8_t b[32]) {
@@ -1373,11 +1481,73 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
         b.adv.push_back(advice_out[i]);
     }
     bool ok = false;
-    b.precompute_denominators(load_le(pubkey_x), load_le(pubkey_y), load_le(r), load_le(s), load_le(msg_hash));
-    b.run(load_le(pubkey_x), load_le(pubkey_y), load_le(r), load_le(s), load_le(msg_hash), &ok);
-    if (b.overflow) return ZKW_ERR_UNSUPPORTED;
-    for (unsigned i = 0; i < b.A; i++)
-        if (b.rows[i] != c->st.rows[i]) return ZKW_ERR_STATE;     // the layout is data-independent by construction
+    const U256 vx = load_le(pubkey_x), vy = load_le(pubkey_y), vr = load_le(r), vs = load_le(s), vm = load_le(msg_hash);
+    const bool have_traj = b.precompute_denominators(vx, vy, vr, vs, vm);
+    const unsigned nthreads = have_traj ? synth_threads() : 1;
+    if (nthreads <= 1 || c->st.checkpoints.empty()) {
+        b.run(vx, vy, vr, vs, vm, &ok);
+        if (b.overflow) return ZKW_ERR_UNSUPPORTED;
+        for (unsigned i = 0; i < b.A; i++)
+            if (b.rows[i] != c->st.rows[i]) return ZKW_ERR_STATE;     // the layout is data-independent by construction
+    } else {
+        // prologue here, then the window segments on `nthreads` threads: each starts from the row counters and accumulator
+        // cells recorded by the structure pass and from the accumulator VALUES of the projective pre-pass
+        Builder::RunCtx rc;
+        Builder::EPt acc, facc;
+        b.prologue(vx, vy, vr, vs, vm, rc, acc, facc);
+        const unsigned nseg = b.num_segments(rc.nw), nw = rc.nw;
+        const auto& cps = c->st.checkpoints;
+        if (cps.size() != nseg) return ZKW_ERR_STATE;
+        for (unsigned i = 0; i < b.A; i++)
+            if (b.rows[i] != cps[1].rows[i]) return ZKW_ERR_STATE;
+        uint64_t total = 0;
+        for (unsigned i = 0; i < b.A; i++) total += c->st.rows[i];
+        const uint64_t work = total - cps[1].cells_before;
+        std::vector<unsigned> cut(nthreads + 1, nseg);
+        cut[0] = 1;
+        for (unsigned t = 1, sgm = 1; t < nthreads; t++) {
+            const uint64_t target = cps[1].cells_before + work * t / nthreads;
+            while (sgm < nseg && cps[sgm].cells_before < target) sgm++;
+            cut[t] = sgm;
+        }
+        std::vector<Builder> workers(nthreads, b);        // copies: own cursor, shared output columns and pre-pass results
+        std::vector<bool> oks(nthreads, true);
+        std::vector<char> done_ok(nthreads, 0);
+        auto body = [&](unsigned t) {
+            Builder& w = workers[t];
+            const unsigned s0 = cut[t], s1 = cut[t + 1];
+            if (s0 >= s1) return;
+            const auto& cp = cps[s0];
+            w.rows = cp.rows;
+            w.dinv_next = Builder::first_op_of(s0, nw);
+            Builder::EPt a2 = acc, f2 = facc;
+            if (t > 0) {
+                // accumulators at the start of segment s0: variable part after window min(s0, nw) - 1, fixed part after
+                // window s0 - nw - 1 (or its constant start point)
+                const unsigned va = (s0 < nw ? s0 : nw) - 1;
+                a2.x = w.elem_at(cp.acc_ids, w.traj_acc_x[va]);
+                a2.y = w.elem_at(cp.acc_ids + 4, w.traj_acc_y[va]);
+                if (s0 > nw) {
+                    f2.x = w.elem_at(cp.facc_ids, w.traj_facc_x[s0 - nw - 1]);
+                    f2.y = w.elem_at(cp.facc_ids + 4, w.traj_facc_y[s0 - nw - 1]);
+                }
+            }
+            bool okt = true;
+            w.run_segments(rc, s0, s1, a2, f2, &okt);
+            if (s1 == nseg) done_ok[t] = okt ? 1 : 2;
+        };
+        std::vector<std::thread> threads;
+        for (unsigned t = 1; t < nthreads; t++) threads.emplace_back(body, t);
+        body(0);
+        for (auto& th : threads) th.join();
+        for (unsigned t = 0; t < nthreads; t++) {
+            if (workers[t].overflow) return ZKW_ERR_UNSUPPORTED;
+            if (done_ok[t]) ok = done_ok[t] == 1;
+            // a worker whose pre-computed inverses stopped matching (cannot happen for a consistent trajectory) fell back to
+            // inverting one by one, which is still correct
+        }
+        b.rows.assign(c->st.rows.begin(), c->st.rows.begin() + b.A);
+    }
     if (b.L) {
         const std::vector<uint32_t>& lk = c->st.lookups;
         for (size_t i = 0; i < lk.size(); i++) memcpy(b.adv[b.A + i % b.L] + 4 * (i / b.L), b.at(lk[i]), 32);
