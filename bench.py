@@ -230,20 +230,28 @@ class HotPathProof:
 
 
 class HostAbiProof:
-    """The same sequence through the host-pointer C ABI (pinned host buffers): what a drop-in FFI
-    call from halo2_proofs pays per best_multiexp / best_fft / evaluate_h call."""
+    """The same sequence through the host-pointer C ABI - what a drop-in FFI call from halo2_proofs pays per best_multiexp /
+    best_fft / evaluate_h call - with every caller buffer in page-locked host memory and reused across steps (inputs AND
+    outputs: the in-place transforms work on the caller's array, like upstream's `&mut [F]`)."""
 
     def __init__(self, zkw, ctx, torch, dev_state: HotPathProof):
         self.zkw, self.ctx, self.s = zkw, ctx, dev_state
+        self.torch = torch
 
         def pinned(t):
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t)
             return h.numpy().view(np.uint64)
 
+        def pinned_empty(rows):
+            return torch.empty((rows, 4), dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+
         self.lagrange = [pinned(t) for t in dev_state.lagrange]
         self.coeff_polys = [pinned(t) for t in dev_state.coeff_polys]
         self.pk = {k: pinned(v) for k, v in dev_state.pk.items()}
+        self.work = [pinned_empty(dev_state.n) for _ in self.lagrange]
+        self.ext = [pinned_empty(dev_state.en) for _ in self.lagrange]
+        self.h = pinned_empty(dev_state.en)
         self.h2d = 0
         self.d2h = 0
 
@@ -255,17 +263,18 @@ class HostAbiProof:
         for col in self.lagrange:
             out.append(ctx.msm(col, which=z.BASES_G_LAGRANGE)); h2d += n * 32; d2h += 96
         out.append(ctx.msm(self.coeff_polys[0], which=z.BASES_G)); h2d += n * 32; d2h += 96
-        ext = []
-        for col in self.lagrange:
-            c = ctx.lagrange_to_coeff(col); h2d += n * 32; d2h += n * 32
-            ext.append(ctx.coeff_to_extended(c, ek)); h2d += n * 32; d2h += en * 32
+        for col, w, e in zip(self.lagrange, self.work, self.ext):
+            w[:] = col                                         # upstream's lagrange_to_coeff consumes its argument
+            ctx.lagrange_to_coeff(w, inplace=True); h2d += n * 32; d2h += n * 32
+            ctx.coeff_to_extended(w, ek, out=e); h2d += n * 32; d2h += en * 32
+        ext = self.ext
         cols = {"advice": [ext[0]], "constants": [self.pk["constants"]], "table": self.pk["table"],
                 "q_enable": [self.pk["q_enable"]], "q_lookup": self.pk["q_lookup"],
                 "sigma": [self.pk["sigma0"], self.pk["sigma1"]], "perm_z": [ext[3]],
                 "lookup_z": [ext[4]], "lookup_a": [ext[1]], "lookup_s": [ext[2]],
                 "l0": self.pk["l0"], "l_last": self.pk["l_last"], "l_active": self.pk["l_active"]}
-        h = ctx.quotient(s.shape, cols, s.challenges); h2d += 14 * en * 32; d2h += en * 32
-        hc = ctx.extended_to_coeff(h); h2d += en * 32; d2h += en * 32
+        h = ctx.quotient(s.shape, cols, s.challenges, out=self.h); h2d += 14 * en * 32; d2h += en * 32
+        hc = ctx.extended_to_coeff(h, inplace=True); h2d += en * 32; d2h += en * 32
         for i in range(4):
             out.append(ctx.msm(hc[i * n:(i + 1) * n], which=z.BASES_G)); h2d += n * 32; d2h += 96
         for p in self.coeff_polys[1:]:
@@ -553,7 +562,7 @@ def run_b200(args):
             hctx.sync()
             e2e["three_seam"] = {"value": 2 / (time.perf_counter() - t0), "unit": UNIT, "h2d_bytes_per_step": host.h2d, "d2h_bytes_per_step": host.d2h,
                                  "path": "host-pointer C ABI, one call per upstream function (15 zkw_msm_bn254_g1, 5 zkw_lagrange_to_coeff, "
-                                         "5 zkw_coeff_to_extended, zkw_quotient_ecdsa, zkw_extended_to_coeff), caller buffers in host memory"}
+                                         "5 zkw_coeff_to_extended, zkw_quotient_ecdsa, zkw_extended_to_coeff), every caller buffer in page-locked host memory"}
             del host, hs
             hctx.close()
     elif not args.no_e2e:

@@ -442,6 +442,90 @@ struct Fp {
 #endif
     }
 
+    // ---- Harvey-style butterfly arithmetic: values in [0, 4m) (4m < 2^256 for both BN254 moduli) -------------------------
+    // The NTT keeps its elements in [0, 4m) between stages: per butterfly ONE conditional subtraction (of 2m, on the
+    // untwiddled input) instead of three (product, sum, difference).  mul_lazy accepts a < 4m, b < m: a*b/R + m < 2m.
+    // [0, 4m) -> [0, 2m)
+    __device__ __forceinline__ Fp reduced_2m() const {
+#ifndef __CUDA_ARCH__
+        return *this;
+#else
+        uint32_t t[8], borrow;
+        asm("sub.cc.u32 %0, %9, %17;\n\t"
+            "subc.cc.u32 %1, %10, %18;\n\t"
+            "subc.cc.u32 %2, %11, %19;\n\t"
+            "subc.cc.u32 %3, %12, %20;\n\t"
+            "subc.cc.u32 %4, %13, %21;\n\t"
+            "subc.cc.u32 %5, %14, %22;\n\t"
+            "subc.cc.u32 %6, %15, %23;\n\t"
+            "subc.cc.u32 %7, %16, %24;\n\t"
+            "subc.u32 %8, 0, 0;"
+            : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+            : "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]),
+              "r"(mod2(0)), "r"(mod2(1)), "r"(mod2(2)), "r"(mod2(3)), "r"(mod2(4)), "r"(mod2(5)), "r"(mod2(6)), "r"(mod2(7)));
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; i++) r.l[i] = borrow ? l[i] : t[i];
+        return r;
+#endif
+    }
+    // a + b with no reduction (the caller guarantees a + b < 2^256)
+    __device__ __forceinline__ static Fp add_raw(const Fp& a, const Fp& b) {
+        Fp r;
+#ifdef __CUDA_ARCH__
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
+        r = a + b;
+#endif
+        return r;
+    }
+    // a - b + 2m for a, b < 2m: in (0, 4m), no condition
+    __device__ __forceinline__ static Fp sub_plus_2m(const Fp& a, const Fp& b) {
+        Fp r;
+#ifdef __CUDA_ARCH__
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]),
+              "r"(mod2(0)), "r"(mod2(1)), "r"(mod2(2)), "r"(mod2(3)), "r"(mod2(4)), "r"(mod2(5)), "r"(mod2(6)), "r"(mod2(7)));
+        asm("sub.cc.u32 %0, %0, %8;\n\t"
+            "subc.cc.u32 %1, %1, %9;\n\t"
+            "subc.cc.u32 %2, %2, %10;\n\t"
+            "subc.cc.u32 %3, %3, %11;\n\t"
+            "subc.cc.u32 %4, %4, %12;\n\t"
+            "subc.cc.u32 %5, %5, %13;\n\t"
+            "subc.cc.u32 %6, %6, %14;\n\t"
+            "subc.u32 %7, %7, %15;"
+            : "+r"(r.l[0]), "+r"(r.l[1]), "+r"(r.l[2]), "+r"(r.l[3]), "+r"(r.l[4]), "+r"(r.l[5]), "+r"(r.l[6]), "+r"(r.l[7])
+            : "r"(b.l[0]), "r"(b.l[1]), "r"(b.l[2]), "r"(b.l[3]), "r"(b.l[4]), "r"(b.l[5]), "r"(b.l[6]), "r"(b.l[7]));
+#else
+        r = a - b;
+#endif
+        return r;
+    }
+    // [0, 4m) -> [0, m)
+    __device__ __forceinline__ Fp normalized_4m() const {
+        Fp r = reduced_2m();
+        r.reduce_once();
+        return r;
+    }
+
     __host__ __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
     __host__ __device__ __forceinline__ Fp from_mont() const {
         Fp o = zero();

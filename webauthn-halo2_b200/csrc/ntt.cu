@@ -56,6 +56,7 @@ struct NttPassArgs {
     int first;       // gather with bit-reversed index
     int coset;       // first pass: multiply source element j by zeta^(j mod 3)
     int scale;       // last pass: multiply output element i by scale3[i mod 3]
+    int last;        // last pass: outputs leave the lazy range [0, 4r) for [0, r)
     Fr zeta, zeta2;
     Fr scale3[3];
     const uint4* stw;   // staged twiddles of this pass's LAST stage, one contiguous block per tile group, or nullptr
@@ -101,9 +102,10 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
             for (int e = 0; e < (1 << R); e++) {
                 if (e & (1 << u)) continue;
                 const unsigned el = e & ((1 << u) - 1);
+                // elements live in [0, 4r) between stages (Harvey): one conditional subtraction per butterfly
                 Fr tv;
                 if (s + u == 0) {
-                    tv = x[e | (1 << u)];  // stage 0: every twiddle is 1
+                    tv = x[e | (1 << u)].reduced_2m();  // stage 0: every twiddle is 1
                 } else {
 #ifdef ZKW_NTT_FAKE_TW   // timing experiment only (wrong results): every twiddle load hits L1
                     const unsigned idx = ((jm + (el << s)) << sh) & 63u;
@@ -113,11 +115,11 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
                     Fr w;
                     if (u == R - 1 && tlo) w = lds_fr(tlo, thi, (int)((((unsigned)glow | (el << t)) << C) + cc));
                     else w = Fr::load_nc(a.tw + 2 * (size_t)idx);
-                    tv = x[e | (1 << u)] * w;
+                    tv = Fr::mul_lazy(x[e | (1 << u)], w);   // < 2r for an input below 4r and a canonical twiddle
                 }
-                Fr uu = x[e];
-                x[e] = uu + tv;
-                x[e | (1 << u)] = uu - tv;
+                const Fr uu = x[e].reduced_2m();
+                x[e] = Fr::add_raw(uu, tv);                      // < 4r
+                x[e | (1 << u)] = Fr::sub_plus_2m(uu, tv);       // < 4r
             }
         }
 #pragma unroll
@@ -189,7 +191,10 @@ __global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kern
         const unsigned c = (tile << C) + cc;
         const size_t i = ((size_t)(c >> a.s0) << (a.s0 + a.B)) | ((size_t)mid << a.s0) | (c & ((1u << a.s0) - 1u));
         Fr v = lds_fr(slo, shi, (mid << C) + cc);
-        if (a.scale) v = v * a.scale3[i % 3];
+        if (a.last) {        // leave the lazy range: canonical output
+            if (a.scale) v = v * a.scale3[i % 3];               // Montgomery product of v < 4r with a canonical scale: < r
+            else v = v.normalized_4m();
+        }
         v.store(a.dst + 2 * i);
     }
 }
@@ -381,6 +386,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         a.B = B;
         a.first = (p == 0);
         a.scale = (p == npass - 1 && scale3) ? 1 : 0;
+        a.last = (p == npass - 1) ? 1 : 0;
         uint64_t* out = dst_dev;
         if (p == 0 && tmp && npass > 1) out = tmp;             // a -> tmp, later passes tmp -> ... -> a
         if (p > 0 && p < npass - 1 && tmp) out = tmp;          // middle passes stay in tmp (tile-local in place)

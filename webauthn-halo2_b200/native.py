@@ -380,8 +380,10 @@ class Context:
         self._check(self.lib.zkw_ntt_bn254_fr_dev(self.h, _addr(a_dev), C.c_uint(log_n), _p(om), _p(sc) if sc is not None else None),
                     "zkw_ntt_bn254_fr_dev")
 
-    def lagrange_to_coeff(self, a: np.ndarray) -> np.ndarray:
-        a = np.array(_as_u64(a, 4), copy=True)
+    def lagrange_to_coeff(self, a: np.ndarray, inplace: bool = False) -> np.ndarray:
+        """inplace=True transforms the caller's (C-contiguous uint64) array itself, as the C ABI does - no copy, and page-locked
+        caller memory (Context.host_array) keeps its transfer speed."""
+        a = _as_u64(a, 4) if inplace else np.array(_as_u64(a, 4), copy=True)
         k = a.shape[0].bit_length() - 1
         self._check(self.lib.zkw_lagrange_to_coeff(self.h, _p(a), C.c_uint(k)), "zkw_lagrange_to_coeff")
         return a
@@ -392,15 +394,18 @@ class Context:
         self._check(self.lib.zkw_coeff_to_lagrange(self.h, _p(a), C.c_uint(k)), "zkw_coeff_to_lagrange")
         return a
 
-    def coeff_to_extended(self, a: np.ndarray, ext_k: int) -> np.ndarray:
+    def coeff_to_extended(self, a: np.ndarray, ext_k: int, out: np.ndarray | None = None) -> np.ndarray:
         a = _as_u64(a, 4)
         k = a.shape[0].bit_length() - 1
-        out = np.zeros((1 << ext_k, 4), dtype=np.uint64)
+        if out is None:
+            out = np.zeros((1 << ext_k, 4), dtype=np.uint64)
+        elif out.shape != (1 << ext_k, 4) or out.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise ValueError("coeff_to_extended: out must be a C-contiguous (2^ext_k, 4) uint64 array")
         self._check(self.lib.zkw_coeff_to_extended(self.h, _p(a), C.c_uint(k), C.c_uint(ext_k), _p(out)), "zkw_coeff_to_extended")
         return out
 
-    def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
-        a = np.array(_as_u64(a, 4), copy=True)
+    def extended_to_coeff(self, a: np.ndarray, inplace: bool = False) -> np.ndarray:
+        a = _as_u64(a, 4) if inplace else np.array(_as_u64(a, 4), copy=True)
         ek = a.shape[0].bit_length() - 1
         self._check(self.lib.zkw_extended_to_coeff(self.h, _p(a), C.c_uint(ek)), "zkw_extended_to_coeff")
         return a
@@ -446,13 +451,16 @@ class Context:
             getattr(q, name)[:] = [int(x) for x in v]
         return q, keep
 
-    def quotient(self, shape: CircuitShape, cols: dict, challenges: dict) -> np.ndarray:
+    def quotient(self, shape: CircuitShape, cols: dict, challenges: dict, out: np.ndarray | None = None) -> np.ndarray:
         """cols: name -> (2^ext_k, 4) array, or list of them for advice / constants / q_enable / sigma /
-        perm_z / lookup_z / lookup_a / lookup_s.  Returns h on the extended coset."""
+        perm_z / lookup_z / lookup_a / lookup_s.  Returns h on the extended coset (written into `out` if given)."""
         cols = {k: ([_as_u64(x, 4) for x in v] if isinstance(v, (list, tuple)) else (_as_u64(v, 4) if v is not None else None))
                 for k, v in cols.items()}
         q, keep = self._quotient_struct(shape, cols, challenges, _p)
-        out = np.zeros((1 << shape.ext_k, 4), dtype=np.uint64)
+        if out is None:
+            out = np.zeros((1 << shape.ext_k, 4), dtype=np.uint64)
+        elif out.shape != (1 << shape.ext_k, 4) or out.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise ValueError("quotient: out must be a C-contiguous (2^ext_k, 4) uint64 array")
         self._check(self.lib.zkw_quotient_ecdsa(self.h, C.byref(q), _p(out)), "zkw_quotient_ecdsa")
         del keep
         return out
