@@ -228,6 +228,11 @@ int zkw_ctx_create(int device, zkw_ctx** out) {
     if (e != cudaSuccess) { int rc = set_cuda_error(ctx, e, "ctx init"); delete ctx; return rc; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    // experiment knob (MSM traffic): L2 fetch granularity in bytes (32 / 64 / 128) for this device
+    if (const char* g = getenv("ZKW_L2_FETCH_GRANULARITY")) {
+        const int v = atoi(g);
+        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    }
     const char* env = getenv("ZKW_MSM_WINDOW_BITS");
     if (env) ctx->msm_window_bits = atoi(env);
     env = getenv("ZKW_MSM_PRECOMPUTE");
