@@ -255,6 +255,15 @@ int zkw_create_proof_ex(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* a
 int zkw_create_proof_seeded(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
                             const uint8_t seed[32], int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
 
+/* The same, with the witness still being produced while the proof starts: the witness-independent device work (the
+ * vanishing argument's random polynomial and its commitment, one MSM) is launched first, then `ready(user)` is called once
+ * on the calling thread and must return ZKW_OK when the advice arrays may be read (or an error, which aborts the proof
+ * and is returned).  zkw_prover_prove uses it to hide the host-side witness synthesis behind that MSM. */
+typedef int (*zkw_advice_ready_fn)(void* user);
+int zkw_create_proof_overlapped(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows,
+                                const uint8_t seed[32], int transcript, unsigned flags, zkw_advice_ready_fn ready, void* user,
+                                uint8_t* out, size_t out_cap, size_t* out_len);
+
 /* Host-side witness synthesis for the shape-identical synthetic ECDSA circuit (stands in for
  * ECDSACircuit::synthesize, halo2-circuits/src/ecc/ecdsa_p256.rs:117-206, whose halo2-ecc chips are un-vendored):
  * fills cols_out[c] (c < num_advice: 4 * floor((2^k - blinding_factors - 1) / 4) cells; lookup-advice columns:

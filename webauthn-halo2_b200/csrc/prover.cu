@@ -650,7 +650,8 @@ int zkw_pk_read(zkw_ctx* ctx, const char* path, zkw_pk** out) {
 // usable rows are zero (unassigned cells), the last blinding_factors+1 rows are blinding.
 // transcript: 0 = Blake2b/Challenge255 (compressed points), 1 = EVM/keccak (uncompressed).
 static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const RandKey& seed,
-                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len);
+                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len, zkw_advice_ready_fn ready = nullptr,
+                             void* ready_user = nullptr);
 
 // 64-bit seeds (deterministic streams for tests and A/B runs) are widened with zeros; production callers pass 32
 // bytes from the OS through zkw_create_proof_seeded
@@ -673,8 +674,17 @@ int zkw_create_proof_seeded(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* cons
     return create_proof_impl(ctx, pk, advice, advice_rows, key, transcript, flags, out, out_cap, out_len);
 }
 
+int zkw_create_proof_overlapped(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const uint8_t seed[32],
+                                int transcript, unsigned flags, zkw_advice_ready_fn ready, void* user, uint8_t* out, size_t out_cap, size_t* out_len) {
+    if (!seed) return ZKW_ERR_INVALID;
+    RandKey key;
+    memcpy(key.w, seed, 32);
+    return create_proof_impl(ctx, pk, advice, advice_rows, key, transcript, flags, out, out_cap, out_len, ready, user);
+}
+
 static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* const* advice, const size_t* advice_rows, const RandKey& seed,
-                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len) {
+                             int transcript, unsigned flags, uint8_t* out, size_t out_cap, size_t* out_len, zkw_advice_ready_fn ready,
+                             void* ready_user) {
     if (!ctx || !pk || !advice || !advice_rows || !out_len || (transcript != 0 && transcript != 1)) return ZKW_ERR_INVALID;
     const bool adv_on_device = flags & ZKW_ADVICE_ON_DEVICE, adv_canonical = flags & ZKW_ADVICE_CANONICAL, shplonk = flags & ZKW_MULTIOPEN_SHPLONK,
                adv_u64 = flags & ZKW_ADVICE_U64;
@@ -715,6 +725,17 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     std::vector<uint64_t*> adv_cf(NA), perm_z_cf(nsets), lk_z_cf(nlk), lk_a_cf(nlk), lk_s_cf(nlk);
     std::vector<const uint64_t*> e_adv(NA), e_pz(nsets), e_lz(nlk), e_la(nlk), e_ls(nlk);
 
+    // ---- 0. witness-independent work first: the vanishing argument's random polynomial and its commitment (absorbed by
+    // the transcript after the grand products).  With zkw_create_proof_overlapped the caller is still synthesising the
+    // witness on the host while this MSM runs; `ready` blocks until the advice columns may be read.
+    LanePipe pipe(ctx, tr, n);
+    uint64_t* random_poly;
+    int t_random;
+    ZKW_TRY(sc.get(vb, (void**)&random_poly));
+    ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
+    ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
+    if (ready) ZKW_TRY(ready(ready_user));
+
     // ---- 1. advice ----
     std::vector<uint64_t*> adv(NA);
     for (unsigned c = 0; c < NA; c++) {
@@ -744,7 +765,6 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     // its own MSM lane: the advice columns, the permuted lookup columns (single-expression lookups: the theta
     // compression is the identity, so A' and S' are functions of the witness alone) and the random polynomial of
     // the vanishing argument.  The transcript still absorbs them in upstream's order (pipe.write below).
-    LanePipe pipe(ctx, tr, n);
     std::vector<int> t_adv(NA), t_lk;
     for (unsigned c = 0; c < NA; c++) ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, adv[c], &t_adv[c]));
 
@@ -793,13 +813,6 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
             t_lk.push_back(ta); t_lk.push_back(ts);
         }
     }
-    // vanishing argument: the random polynomial (committed after the grand products, computed now)
-    uint64_t* random_poly;
-    int t_random;
-    ZKW_TRY(sc.get(vb, (void**)&random_poly));
-    ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
-    ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
-
     for (int t : t_adv) ZKW_TRY(pipe.write(t));
     const Fr theta = tr.squeeze();
     (void)theta;

@@ -142,17 +142,32 @@ extern "C" int zkw_prover_prove(zkw_prover* p, const uint8_t assertion[160], con
     if (seed32_or_null) memcpy(seed, seed32_or_null, 32);
     else if (!os_random(seed, 32)) return ZKW_ERR_STATE;            // OsRng (ecdsa_p256.rs:362,412)
     std::lock_guard<std::mutex> lock(p->mu);
-    int ok = 0;
-    timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    int rc = zkw_ecdsa_synthesize(p->circuit, x, y, r, s, m, p->staging.data(), nullptr, &ok);
-    clock_gettime(CLOCK_MONOTONIC, &t1);
-    p->last_synth_ms = 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec);
-    if (rc != ZKW_OK) return rc;
-    if (!ok) return ZKW_ERR_SIGNATURE;                               // no satisfying assignment exists: prove nothing
+    // the witness is synthesised on a host thread (which fans out to ZKW_SYNTH_THREADS more) while the device already works
+    // on the proof's witness-independent part; the proof picks the columns up when `ready` returns
+    struct Synth {
+        zkw_prover* p;
+        const uint8_t *x, *y, *r, *s, *m;
+        int rc = ZKW_OK, ok = 0;
+        std::thread th;
+        static int ready(void* u) {
+            Synth* self = (Synth*)u;
+            if (self->th.joinable()) self->th.join();
+            if (self->rc != ZKW_OK) return self->rc;
+            return self->ok ? ZKW_OK : ZKW_ERR_SIGNATURE;            // no satisfying assignment exists: prove nothing
+        }
+    } sy{p, x, y, r, s, m};
+    sy.th = std::thread([&sy] {
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        sy.rc = zkw_ecdsa_synthesize(sy.p->circuit, sy.x, sy.y, sy.r, sy.s, sy.m, sy.p->staging.data(), nullptr, &sy.ok);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        sy.p->last_synth_ms = 1e3 * (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_nsec - t0.tv_nsec);
+    });
     flags &= ~(unsigned)(ZKW_ADVICE_ON_DEVICE | ZKW_ADVICE_U64);
-    return zkw_create_proof_seeded(p->ctx, p->pk, p->staging.data(), p->rows.data(), seed, transcript, flags | ZKW_ADVICE_CANONICAL, out, out_cap,
-                                   out_len);
+    int rc = zkw_create_proof_overlapped(p->ctx, p->pk, p->staging.data(), p->rows.data(), seed, transcript, flags | ZKW_ADVICE_CANONICAL,
+                                         &Synth::ready, &sy, out, out_cap, out_len);
+    if (sy.th.joinable()) sy.th.join();                              // an early error never reached `ready`
+    return rc;
 }
 
 extern "C" int zkw_prove_batch(zkw_prover* const* workers, size_t nworkers, const uint8_t* assertions, size_t count, const uint8_t* seeds32_or_null,

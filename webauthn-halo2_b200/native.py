@@ -45,7 +45,7 @@ EXPORTS = [
     "zkw_extended_to_coeff_dev", "zkw_quotient_ecdsa", "zkw_quotient_ecdsa_dev", "zkw_dev_alloc", "zkw_dev_free",
     "zkw_memcpy_h2d", "zkw_memcpy_d2h", "zkw_srs_setup", "zkw_srs_get", "zkw_g1_fixed_base_mul",
     "zkw_profile_enable", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
-    "zkw_keygen", "zkw_pk_destroy", "zkw_pk_info", "zkw_pk_vk", "zkw_create_proof", "zkw_create_proof_ex", "zkw_create_proof_seeded", "zkw_fr_to_mont", "zkw_fr_from_mont",
+    "zkw_keygen", "zkw_pk_destroy", "zkw_pk_info", "zkw_pk_vk", "zkw_create_proof", "zkw_create_proof_ex", "zkw_create_proof_seeded", "zkw_create_proof_overlapped", "zkw_fr_to_mont", "zkw_fr_from_mont",
     "zkw_synth_witness", "zkw_host_alloc", "zkw_host_free",
     "zkw_ecdsa_circuit_new", "zkw_ecdsa_circuit_free", "zkw_ecdsa_circuit_shape", "zkw_ecdsa_circuit_rows", "zkw_ecdsa_circuit_fixed",
     "zkw_ecdsa_circuit_permutation", "zkw_ecdsa_synthesize",
