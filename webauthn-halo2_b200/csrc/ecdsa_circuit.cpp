@@ -1511,7 +1511,6 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
             cut[t] = sgm;
         }
         std::vector<Builder> workers(nthreads, b);        // copies: own cursor, shared output columns and pre-pass results
-        std::vector<bool> oks(nthreads, true);
         std::vector<char> done_ok(nthreads, 0);
         auto body = [&](unsigned t) {
             Builder& w = workers[t];
