@@ -67,6 +67,36 @@ def test_invalid_signature_has_no_satisfying_assignment(what):
     assert errs and all(e[0] == "copy" for e in errs)     # every relation holds except R.x == r
 
 
+def _sign(sk, k, m):
+    from tests.assertions import G, mul
+    pk = mul(G, sk)
+    r = mul(G, k)[0] % P256_N
+    s = pow(k, -1, P256_N) * (m + r * sk) % P256_N
+    return {"pubkey_x": pk[0], "pubkey_y": pk[1], "r": r, "s": s, "msg_hash": m}
+
+
+@pytest.mark.parametrize("name,sk,k,m", [
+    ("zero message hash (u1 = 0: every fixed-base window is zero)", 0x1234567, 0x7654321, 0),
+    ("secret key 1 (PK = G)", 1, 5, 12345),
+    ("tiny nonce and message (u2 has long zero runs)", 3, 1, 1),
+    ("top-heavy values", P256_N - 2, P256_N - 3, P256_N - 1),
+])
+def test_edge_case_signatures_are_satisfied(zkw, name, sk, k, m):
+    """Valid signatures at the corners of the scalar range: the offset points keep every accumulator away from the identity,
+    the oracle's assignment is satisfied, and the product's synthesis agrees with it and reports the signature as valid."""
+    a = _sign(sk, k, m)
+    assert verify_ints(a), name
+    b = _synth(17, a)
+    assert ec.check(b) == [], name
+    c = zkw.EcdsaCircuit(zkw.CircuitParams.for_degree(17))
+    try:
+        adv = c.synthesize(*[a[key].to_bytes(32, "little") for key in ("pubkey_x", "pubkey_y", "r", "s", "msg_hash")])
+        for i, col in enumerate(adv):
+            assert _ints(col) == b.advice[i][: col.shape[0]], (name, i)
+    finally:
+        c.close()
+
+
 def test_degenerate_inputs_are_unsatisfiable_not_crashes():
     a = signed_ints(7)
     for key, val in (("s", 0), ("r", 0), ("r", P256_N), ("s", P256_N + 5)):
