@@ -1,27 +1,29 @@
 #!/usr/bin/env python
-"""bench.py — proofs/s for the P-256 ECDSA circuit's prover hot path at k = 19 on N B200s.
+"""bench.py — proofs/s for the P-256 ECDSA circuit's prover at k = 19 on N B200s.
 
-Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
-line from rank 0.  A "step" is one pass of the hot path for ONE proof at the k = 19 shape of
-halo2-circuits/src/configs/bench_ecdsa.config:1 (1 advice / 1 lookup / 1 fixed column; degree-5
-constraint system, extended domain 2^21) with the EVM-transcript (GWC) opening count of
-BASELINE.json configs[1]:
+Contract (see the task statement): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.
 
-    15 MSMs of 2^19 points   (advice, A', S', Z_perm, Z_lookup over g_lagrange; random poly,
-                              4 quotient pieces, 5 GWC witnesses over g)
-     5 iNTT(2^19)            lagrange_to_coeff of advice, A', S', Z_perm, Z_lookup
-     5 NTT(2^19 -> 2^21)     coeff_to_extended of the same
-     1 quotient evaluation   2^21 rows, 14 input cosets
-     1 iNTT(2^21)            extended_to_coeff of h
+A "step" is ONE complete proof (`--workload proof`, the default): zkw_create_proof on the device for the k = 19 shape of
+halo2-circuits/src/configs/bench_ecdsa.config:1 (1 advice / 1 lookup / 1 fixed column; degree-5 constraint system, extended
+domain 2^21), EVM transcript + GWC (BASELINE.json configs[1]), over the REAL ECDSA verification circuit's witness for a
+synthetic signed WebAuthn assertion: 15 MSMs of 2^19 points, 5 iNTT(2^19), 5 coset NTTs 2^19 -> 2^21, the quotient over 2^21
+rows and 14 cosets, 1 iNTT(2^21), plus lookup permutation, grand products, evaluations, openings and the transcript.
 
-on synthetic uniformly random columns (the worst case for the MSM: every window of every scalar
-is populated).  `value` times this with all inputs resident in HBM; `e2e` times the same sequence
-through the host-pointer C ABI (what a drop-in FFI call from halo2_proofs pays), host<->device
-copies included.  `--impl reference` times the CPU oracle (a restatement of the upstream CPU
-algorithms; the Rust prover cannot be built here) on the host cores.
+    value       proofs/s with the advice column already resident in HBM (device-timed, CUDA events, max over ranks)
+    e2e         the same through the public API (ProverState.prove -> zkw_prover_prove): assertion bytes in host memory ->
+                witness synthesis on the host -> H2D of the assigned cells -> proof bytes back; `e2e.three_seam` is the
+                hot-path call sequence through the three host-pointer seams a [patch]ed halo2_proofs would bind
+    batch       BASELINE configs[2]/[3]: 64 proofs per GPU through zkw_prove_batch with three provers in flight
+    split_msm   (N > 1) BASELINE configs[4]'s multi-GPU leg: one 2^20 / 2^22-point MSM split over the ranks
+    roofline    the dominant kernel (msm_accumulate_kernel): algorithmic bytes / measured launch time against the measured
+                HBM copy bandwidth; DRAM traffic and the ALU ceiling are read from the committed ncu export / profiles
+    cpu_baseline / --impl reference
+                the CPU oracle (a C restatement of the upstream CPU algorithms; the Rust prover cannot be built here)
+                running the hot-path call sequence of one whole proof per step on the host cores
 
-One process per GPU; independent proofs shard with no collective (torch.distributed is used only
-for the barrier and the max-over-ranks of the elapsed time).
+`--workload hotpath` times the bare MSM / NTT / quotient sequence on uniformly random columns instead (round 1's first bench).
+One process per GPU; independent proofs shard with no collective (torch.distributed is used only for the barrier, the
+max-over-ranks of the elapsed time and the optional split-MSM leg).
 """
 from __future__ import annotations
 
