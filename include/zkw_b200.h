@@ -70,6 +70,9 @@ uint64_t zkw_ctx_launch_count(zkw_ctx* ctx);
  * roofline of the dominant kernel.  Kernel names are the __global__ function names
  * ("msm_accumulate_kernel", "ntt_pass_kernel", "quotient_kernel", ...). */
 int zkw_profile_enable(zkw_ctx* ctx, int on);
+/* Time only launches of one kernel (NULL: every kernel): two events per launch perturb a proof of 215 launches by ~1 ms,
+ * bench.py times just the dominant kernel inside its timed region. */
+int zkw_profile_filter(zkw_ctx* ctx, const char* kernel_or_null);
 int zkw_profile_reset(zkw_ctx* ctx);
 int zkw_profile_read(zkw_ctx* ctx, const char* kernel, double* total_ms, uint64_t* launches);
 int zkw_profile_names(zkw_ctx* ctx, char* buf, size_t cap); /* comma-separated names seen so far */

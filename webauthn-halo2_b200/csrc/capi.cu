@@ -105,7 +105,7 @@ static cudaEvent_t take_event(zkw_ctx* ctx) {
 }
 
 ProfScope::ProfScope(zkw_ctx* c, const char* name, cudaStream_t s) : ctx(c), stream(s ? s : c->stream) {
-    if (!c->profiling) return;
+    if (!c->profiling || (!c->prof_filter.empty() && c->prof_filter != name)) return;
     cudaEvent_t start = take_event(c);
     stop = take_event(c);
     if (!start || !stop) { stop = nullptr; return; }
@@ -293,6 +293,12 @@ int zkw_profile_enable(zkw_ctx* ctx, int on) {
     if (!ctx) return ZKW_ERR_INVALID;
     profile_collect(ctx);
     ctx->profiling = on != 0;
+    return ZKW_OK;
+}
+int zkw_profile_filter(zkw_ctx* ctx, const char* kernel_or_null) {
+    if (!ctx) return ZKW_ERR_INVALID;
+    profile_collect(ctx);
+    ctx->prof_filter = kernel_or_null ? kernel_or_null : "";
     return ZKW_OK;
 }
 int zkw_profile_reset(zkw_ctx* ctx) {

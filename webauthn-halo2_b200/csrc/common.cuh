@@ -90,6 +90,7 @@ struct zkw_ctx {
 
     // optional per-kernel timing (CUDA events on the ctx stream), off by default
     bool profiling = false;
+    std::string prof_filter;          // non-empty: only launches of this kernel are timed (zkw_profile_filter)
     struct ProfRec { const char* name; cudaEvent_t start, stop; cudaStream_t stream; };
     cudaEvent_t prof_ref = nullptr;      // timeline origin (ZKW_TIMELINE)
     std::vector<ProfRec> prof_pending;

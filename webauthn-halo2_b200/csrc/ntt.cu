@@ -145,12 +145,46 @@ __global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kern
         bulk_load(tlo, a.stw + 2 * (size_t)(tile & a.stw_group_mask) * stw_entries, (uint32_t)stw_entries * 32u, bar);
     }
     // ---- gather the tile ----
-    for (int q = threadIdx.x; q < tsize; q += kNttThreads) {
-        int mid, cc;
+    // Full tiles (the only case above 2^10 elements) issue all of a thread's loads before touching any of them: 16 128-bit
+    // loads in flight per thread instead of one element at a time (the bit-reversed first pass reads isolated 32-byte
+    // sectors, each a DRAM round trip).
+    auto tile_index = [&](int q, int& mid, int& cc) -> size_t {
         if (a.s0 == 0) { mid = q & ((1 << a.B) - 1); cc = q >> a.B; }
         else { cc = q & ((1 << C) - 1); mid = q >> C; }
         const unsigned c = (tile << C) + cc;
-        const size_t i = ((size_t)(c >> a.s0) << (a.s0 + a.B)) | ((size_t)mid << a.s0) | (c & ((1u << a.s0) - 1u));
+        return ((size_t)(c >> a.s0) << (a.s0 + a.B)) | ((size_t)mid << a.s0) | (c & ((1u << a.s0) - 1u));
+    };
+    if (tsize == (kNttThreads << 3)) {
+        Fr v[8];
+        unsigned src_j[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            int mid, cc;
+            const size_t i = tile_index(threadIdx.x + e * kNttThreads, mid, cc);
+            if (a.first) {
+                const unsigned j = __brev((unsigned)i) >> (32 - a.log_n);
+                src_j[e] = j;
+                v[e] = (j >> a.src_log_n) != 0 ? Fr::zero() : Fr::load(a.src + 2 * (size_t)j);
+            } else {
+                src_j[e] = 0;
+                v[e] = Fr::load(a.src + 2 * i);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            int mid, cc;
+            tile_index(threadIdx.x + e * kNttThreads, mid, cc);
+            if (a.first && a.coset && (src_j[e] >> a.src_log_n) == 0) {
+                const unsigned m3 = src_j[e] % 3u;
+                if (m3 == 1) v[e] = v[e] * a.zeta;
+                else if (m3 == 2) v[e] = v[e] * a.zeta2;
+            }
+            sts_fr(slo, shi, (mid << C) + cc, v[e]);
+        }
+    } else {
+    for (int q = threadIdx.x; q < tsize; q += kNttThreads) {
+        int mid, cc;
+        const size_t i = tile_index(q, mid, cc);
         Fr v;
         if (a.first) {
             const unsigned j = __brev((unsigned)i) >> (32 - a.log_n);
@@ -168,6 +202,7 @@ __global__ void __launch_bounds__(kNttThreads, ZKW_NTT_MIN_BLOCKS) ntt_pass_kern
             v = Fr::load(a.src + 2 * i);
         }
         sts_fr(slo, shi, (mid << C) + cc, v);
+    }
     }
     __syncthreads();
     // ---- butterfly rounds ----

@@ -44,7 +44,7 @@ EXPORTS = [
     "zkw_coeff_to_lagrange_dev", "zkw_coeff_to_extended", "zkw_coeff_to_extended_dev", "zkw_extended_to_coeff",
     "zkw_extended_to_coeff_dev", "zkw_quotient_ecdsa", "zkw_quotient_ecdsa_dev", "zkw_dev_alloc", "zkw_dev_free",
     "zkw_memcpy_h2d", "zkw_memcpy_d2h", "zkw_srs_setup", "zkw_srs_get", "zkw_g1_fixed_base_mul",
-    "zkw_profile_enable", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
+    "zkw_profile_enable", "zkw_profile_filter", "zkw_profile_reset", "zkw_profile_read", "zkw_profile_names",
     "zkw_keygen", "zkw_pk_destroy", "zkw_pk_info", "zkw_pk_vk", "zkw_create_proof", "zkw_create_proof_ex", "zkw_create_proof_seeded", "zkw_create_proof_overlapped", "zkw_fr_to_mont", "zkw_fr_from_mont",
     "zkw_synth_witness", "zkw_host_alloc", "zkw_host_free",
     "zkw_ecdsa_circuit_new", "zkw_ecdsa_circuit_free", "zkw_ecdsa_circuit_shape", "zkw_ecdsa_circuit_rows", "zkw_ecdsa_circuit_fixed",
@@ -134,6 +134,7 @@ def load_library() -> C.CDLL:
     lib.zkw_ctx_destroy.restype = None
     lib.zkw_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.zkw_profile_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    lib.zkw_profile_filter.argtypes = [C.c_void_p, C.c_char_p]
     lib.zkw_synth_witness.argtypes = [C.POINTER(CircuitShape), C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(u64p), C.POINTER(C.c_size_t)]
     lib.zkw_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkw_host_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -289,6 +290,10 @@ class Context:
     # -- per-kernel device timing ------------------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._check(self.lib.zkw_profile_enable(self.h, int(on)), "zkw_profile_enable")
+
+    def profile_filter(self, kernel: str | None):
+        """time only launches of `kernel` (None: all kernels)"""
+        self._check(self.lib.zkw_profile_filter(self.h, kernel.encode() if kernel else None), "zkw_profile_filter")
 
     def profile_reset(self):
         self._check(self.lib.zkw_profile_reset(self.h), "zkw_profile_reset")
