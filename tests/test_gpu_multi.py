@@ -88,3 +88,28 @@ def test_split_msm_and_sharded_proofs_nccl():
             assert st.prove(b"assertion-%d" % i, zkw.TRANSCRIPT_EVM, seed=100 + i).hex() == proofs[i]
     finally:
         st.close()
+
+
+@pytest.mark.skipif(_gpus() < 2, reason="needs 2 GPUs")
+def test_one_process_batch_over_two_gpus():
+    """zkw_prove_batch with provers on two different GPUs, driven by the library's threads from ONE process: every proof is
+    accepted under the (device-independent) verifying key, and both GPUs produced some."""
+    sys.path.insert(0, ROOT)
+    zkw = importlib.import_module("webauthn-halo2_b200")
+    from oracle import cpu, halo2_ref as h
+    pool = zkw.ProverPool(zkw.CircuitParams.for_degree(15), device=[0, 1], workers=2)
+    try:
+        assert [st.ctx.device for st in pool.states] == [0, 0, 1, 1]
+        vks = [st.pk.vk() for st in pool.states]
+        assert all(np.array_equal(v[0], vks[0][0]) and np.array_equal(v[2], vks[0][2]) for v in vks)     # same key on both GPUs
+        assertions = [zkw.synthetic_assertion(500 + i) for i in range(12)]
+        before = [st.ctx.launch_count for st in pool.states]
+        proofs = pool.prove_many(assertions, zkw.TRANSCRIPT_EVM)
+        after = [st.ctx.launch_count for st in pool.states]
+        assert after[0] + after[1] > before[0] + before[1] and after[2] + after[3] > before[2] + before[3]
+        fx, pm, dg = vks[0]
+        vk = h.VerifyingKey(h.Shape(15, 17, 3, 1), [cpu.g1_affine_to_ints(p) for p in fx], [cpu.g1_affine_to_ints(p) for p in pm],
+                            cpu.fr_from_mont(dg.reshape(1, 4))[0])
+        assert all(h.verify_proof(vk, p, "evm", tau=zkw.prover.DEV_TAU_CANONICAL) for p in proofs)
+    finally:
+        pool.close()

@@ -325,8 +325,12 @@ class ProverPool:
     assertion overlaps the device work of the others, and the latency-bound phases of one proof overlap the
     throughput-bound phases of another."""
 
-    def __init__(self, params: CircuitParams, device: int = 0, workers: int = 3, synthetic: bool = False):
-        self.states = [ProverState(params, device, synthetic=synthetic) for _ in range(workers)]
+    def __init__(self, params: CircuitParams, device: int | list[int] = 0, workers: int = 3, synthetic: bool = False):
+        """device: one GPU, or a list of GPUs - `workers` provers on EACH of them, all driven from this process by the
+        library's threads (zkw_prove_batch takes provers on any mix of devices); the one-process-per-GPU layout of bench.py
+        is the alternative."""
+        devices = [device] if isinstance(device, int) else list(device)
+        self.states = [ProverState(params, d, synthetic=synthetic) for d in devices for _ in range(workers)]
 
     def prove_many(self, assertions: list[bytes], transcript: int, seed0: int | None = None) -> list[bytes]:
         """seed0 = None (default): every proof draws its own blinding seed from the OS (the reference's OsRng,
