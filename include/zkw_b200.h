@@ -69,6 +69,10 @@ uint64_t zkw_ctx_launch_count(zkw_ctx* ctx);
 /* Optional per-kernel device timing (CUDA events on the ctx stream), used by bench.py for the
  * roofline of the dominant kernel.  Kernel names are the __global__ function names
  * ("msm_accumulate_kernel", "ntt_pass_kernel", "quotient_kernel", ...). */
+/* Device self-test of the hand-written field arithmetic variants: the dedicated Montgomery squaring against the general
+ * product, limb for limb, on `count` pseudo-random values (plus corner cases) of Fr and Fq; mismatches_out = {Fr, Fq} counts. */
+int zkw_selftest_field(zkw_ctx* ctx, uint64_t seed, unsigned count, unsigned mismatches_out[2]);
+
 int zkw_profile_enable(zkw_ctx* ctx, int on);
 /* Time only launches of one kernel (NULL: every kernel): two events per launch perturb a proof of 215 launches by ~1 ms,
  * bench.py times just the dominant kernel inside its timed region. */

@@ -225,3 +225,11 @@ def test_msm_full_size_k19_matches_oracle_bit_for_bit(zkw, oracle):
             assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], _affine(oracle, oracle.best_multiexp(s, g))), name
     finally:
         c.close()
+
+
+def test_dedicated_squaring_equals_general_product_on_device(ctx):
+    """Fp::sqr_lazy (irregular-row interleaved Montgomery squaring, used twice per bucket addition) against mul_lazy(a, a), limb
+    for limb, on 2^18 pseudo-random values over the whole lazy range [0, 2m) and the corners 0, 1, m - 1, m, m + 1, 2m - 1, for
+    Fr and Fq."""
+    for seed in (1, 2, 0xB200):
+        assert ctx.selftest_field(seed=seed, count=1 << 18) == (0, 0)

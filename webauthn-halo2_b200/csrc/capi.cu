@@ -195,6 +195,47 @@ static int host_transform(zkw_ctx* ctx, const uint64_t* src, size_t n_in, uint64
 }
 
 
+// ---- device self-test of the hand-written field arithmetic variants -------------------------------------------------------
+// sqr_lazy(a) against mul_lazy(a, a) limb for limb, over the whole lazy range [0, 2m) of both fields: pseudo-random values plus
+// the corners 0, 1, m - 1, m, m + 1, 2m - 1.
+template <class F>
+__device__ bool selftest_sqr_one(uint64_t seed, unsigned i) {
+    F a;
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1);
+    for (int j = 0; j < 4; j++) {
+        z += 0x9E3779B97F4A7C15ULL;
+        uint64_t w = z;
+        w = (w ^ (w >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        w = (w ^ (w >> 27)) * 0x94D049BB133111EBULL;
+        w ^= w >> 31;
+        a.l[2 * j] = (uint32_t)w;
+        a.l[2 * j + 1] = (uint32_t)(w >> 32);
+    }
+    a.l[7] &= 0x7FFFFFFFu;                 // < 2^255 < 4m
+    a = a.reduced_2m();                    // [0, 2m)
+    if (i < 6) {
+        F m1 = F::zero() - F::one();        // m - 1
+        F one = F::zero();
+        one.l[0] = 1;                       // the integer 1 (not Montgomery one): any residue will do
+        if (i == 0) a = F::zero();
+        else if (i == 1) a = one;
+        else if (i == 2) a = m1;
+        else if (i == 3) a = F::add_raw(m1, one);                       // m
+        else if (i == 4) a = F::add_raw(F::add_raw(m1, one), one);      // m + 1
+        else a = F::add_raw(F::add_raw(m1, m1), one);                   // 2m - 1
+    }
+    const F s = F::sqr_lazy(a), p = F::mul_lazy(a, a);
+    bool ok = true;
+    for (int j = 0; j < 8; j++) ok = ok && s.l[j] == p.l[j];
+    return ok;
+}
+__global__ void selftest_sqr_kernel(uint64_t seed, unsigned count, unsigned* mismatches) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (!selftest_sqr_one<zkw::Fr>(seed, i)) atomicAdd(&mismatches[0], 1u);
+    if (!selftest_sqr_one<zkw::Fq>(seed ^ 0x5555, i)) atomicAdd(&mismatches[1], 1u);
+}
+
 extern "C" {
 
 const char* zkw_strerror(int status) {
@@ -337,6 +378,21 @@ int zkw_dev_free(zkw_ctx* ctx, void* dev) {
     ZKW_CUDA(ctx, cudaFree(dev));
     return ZKW_OK;
 }
+int zkw_selftest_field(zkw_ctx* ctx, uint64_t seed, unsigned count, unsigned mismatches_out[2]) {
+    CTX_ENTER(ctx);
+    if (!mismatches_out || !count) return ZKW_ERR_INVALID;
+    unsigned* d = nullptr;
+    ZKW_CUDA(ctx, cudaMalloc(&d, 8));
+    ZKW_CUDA(ctx, cudaMemsetAsync(d, 0, 8, ctx->stream));
+    selftest_sqr_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>(seed, count, d);
+    ZKW_LAUNCHED(ctx);
+    cudaError_t e = cudaMemcpyAsync(mismatches_out, d, 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return zkw::set_cuda_error(ctx, e, "zkw_selftest_field");
+    return ZKW_OK;
+}
+
 int zkw_host_alloc(zkw_ctx* ctx, size_t bytes, void** out_host) {
     CTX_ENTER(ctx);
     if (!out_host) return ZKW_ERR_INVALID;

@@ -132,10 +132,16 @@ struct G1Xyzz {
             add_mixed(b, false);
             return;
         }
+#ifdef ZKW_MSM_NO_SQR
         Fq pp = Fq::mul_lazy(p, p);
+        const Fq rr = Fq::mul_lazy(r, r);
+#else
+        Fq pp = Fq::sqr_lazy(p);          // the two squarings of the 8M + 2S addition: 100 wide multiplies instead of 128 each
+        const Fq rr = Fq::sqr_lazy(r);
+#endif
         Fq ppp = Fq::mul_lazy(p, pp);
         Fq q = Fq::mul_lazy(x, pp);
-        Fq x3 = Fq::sub_lazy(Fq::sub_lazy(Fq::mul_lazy(r, r), ppp), Fq::add_lazy(q, q));
+        Fq x3 = Fq::sub_lazy(Fq::sub_lazy(rr, ppp), Fq::add_lazy(q, q));
         y = Fq::sub_lazy(Fq::mul_lazy(r, Fq::sub_lazy(q, x3)), Fq::mul_lazy(y, ppp));
         x = x3;
         zz = Fq::mul_lazy(zz, pp);

@@ -100,6 +100,85 @@ __device__ __forceinline__ void shift_mad_pairs(uint32_t& nA0, uint32_t nB[9], u
     nB[8] = 0;
 }
 
+
+// ---- irregular rows of the squaring (Fp::sqr_lazy): the same two chains with their first S pairs absent ------------------
+// c[2S..8] += x_S*b*2^(64 S) + ... + x_3*b*2^192
+__device__ __forceinline__ void mad_pairs_s1(uint32_t c[9], uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0;\n\t"
+        "madc.hi.cc.u32 %1, %7, %10, %1;\n\t"
+        "madc.lo.cc.u32 %2, %8, %10, %2;\n\t"
+        "madc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+        "madc.lo.cc.u32 %4, %9, %10, %4;\n\t"
+        "madc.hi.cc.u32 %5, %9, %10, %5;\n\t"
+        "addc.u32 %6, %6, 0;"
+        : "+r"(c[2]), "+r"(c[3]), "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8])
+        : "r"(x1), "r"(x2), "r"(x3), "r"(b));
+}
+__device__ __forceinline__ void mad_pairs_s2(uint32_t c[9], uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0;\n\t"
+        "madc.hi.cc.u32 %1, %5, %7, %1;\n\t"
+        "madc.lo.cc.u32 %2, %6, %7, %2;\n\t"
+        "madc.hi.cc.u32 %3, %6, %7, %3;\n\t"
+        "addc.u32 %4, %4, 0;"
+        : "+r"(c[4]), "+r"(c[5]), "+r"(c[6]), "+r"(c[7]), "+r"(c[8])
+        : "r"(x2), "r"(x3), "r"(b));
+}
+__device__ __forceinline__ void mad_pairs_s3(uint32_t c[9], uint32_t x3, uint32_t b) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0;\n\t"
+        "madc.hi.cc.u32 %1, %3, %4, %1;\n\t"
+        "addc.u32 %2, %2, 0;"
+        : "+r"(c[6]), "+r"(c[7]), "+r"(c[8])
+        : "r"(x3), "r"(b));
+}
+// shift_mad_pairs with the first S product pairs absent: those limbs only take the shifted accumulator and the carry
+__device__ __forceinline__ void shift_mad_pairs_s1(uint32_t& nA0, uint32_t nB[9], uint32_t B0, const uint32_t A[9],
+                                                   uint32_t x1, uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("add.cc.u32 %0, %9, %10;\n\t"
+        "addc.cc.u32 %1, %11, 0;\n\t"
+        "addc.cc.u32 %2, %12, 0;\n\t"
+        "madc.lo.cc.u32 %3, %18, %21, %13;\n\t"
+        "madc.hi.cc.u32 %4, %18, %21, %14;\n\t"
+        "madc.lo.cc.u32 %5, %19, %21, %15;\n\t"
+        "madc.hi.cc.u32 %6, %19, %21, %16;\n\t"
+        "madc.lo.cc.u32 %7, %20, %21, %17;\n\t"
+        "madc.hi.u32 %8, %20, %21, 0;"
+        : "=r"(nA0), "=r"(nB[0]), "=r"(nB[1]), "=r"(nB[2]), "=r"(nB[3]), "=r"(nB[4]), "=r"(nB[5]), "=r"(nB[6]), "=r"(nB[7])
+        : "r"(B0), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+          "r"(x1), "r"(x2), "r"(x3), "r"(b));
+    nB[8] = 0;
+}
+__device__ __forceinline__ void shift_mad_pairs_s2(uint32_t& nA0, uint32_t nB[9], uint32_t B0, const uint32_t A[9],
+                                                   uint32_t x2, uint32_t x3, uint32_t b) {
+    asm("add.cc.u32 %0, %9, %10;\n\t"
+        "addc.cc.u32 %1, %11, 0;\n\t"
+        "addc.cc.u32 %2, %12, 0;\n\t"
+        "addc.cc.u32 %3, %13, 0;\n\t"
+        "addc.cc.u32 %4, %14, 0;\n\t"
+        "madc.lo.cc.u32 %5, %18, %20, %15;\n\t"
+        "madc.hi.cc.u32 %6, %18, %20, %16;\n\t"
+        "madc.lo.cc.u32 %7, %19, %20, %17;\n\t"
+        "madc.hi.u32 %8, %19, %20, 0;"
+        : "=r"(nA0), "=r"(nB[0]), "=r"(nB[1]), "=r"(nB[2]), "=r"(nB[3]), "=r"(nB[4]), "=r"(nB[5]), "=r"(nB[6]), "=r"(nB[7])
+        : "r"(B0), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+          "r"(x2), "r"(x3), "r"(b));
+    nB[8] = 0;
+}
+__device__ __forceinline__ void shift_mad_pairs_s3(uint32_t& nA0, uint32_t nB[9], uint32_t B0, const uint32_t A[9], uint32_t x3, uint32_t b) {
+    asm("add.cc.u32 %0, %9, %10;\n\t"
+        "addc.cc.u32 %1, %11, 0;\n\t"
+        "addc.cc.u32 %2, %12, 0;\n\t"
+        "addc.cc.u32 %3, %13, 0;\n\t"
+        "addc.cc.u32 %4, %14, 0;\n\t"
+        "addc.cc.u32 %5, %15, 0;\n\t"
+        "addc.cc.u32 %6, %16, 0;\n\t"
+        "madc.lo.cc.u32 %7, %18, %19, %17;\n\t"
+        "madc.hi.u32 %8, %18, %19, 0;"
+        : "=r"(nA0), "=r"(nB[0]), "=r"(nB[1]), "=r"(nB[2]), "=r"(nB[3]), "=r"(nB[4]), "=r"(nB[5]), "=r"(nB[6]), "=r"(nB[7])
+        : "r"(B0), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+          "r"(x3), "r"(b));
+    nB[8] = 0;
+}
+
 template <class P>
 struct Fp {
     uint32_t l[8];
@@ -311,7 +390,14 @@ struct Fp {
         return r;
 #endif
     }
-    __host__ __device__ __forceinline__ Fp sqr() const { return *this * *this; }
+    // canonical square: on the device the dedicated squaring below (bit-identical to the product, 100 wide multiplies)
+    __host__ __device__ __forceinline__ Fp sqr() const {
+#ifdef __CUDA_ARCH__
+        return sqr_lazy(*this).normalized();
+#else
+        return *this * *this;
+#endif
+    }
 
     // ---- lazily reduced arithmetic: values in [0, 2m) ------------------------------------------------------
     // 4m < 2^256 for both BN254 moduli, so a Montgomery product of two values below 2m is below 2m WITHOUT the
@@ -358,6 +444,103 @@ struct Fp {
 #pragma unroll
             for (int k = 0; k < 9; k++) { A[k] = nA[k]; B[k] = nB[k]; }
         }
+        Fp r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+              "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
+        return r;
+#endif
+    }
+    // a * a * R^-1 mod m for a < 2m; result < 2m - bit-identical to mul_lazy(a, a), with 100 wide multiplies instead of 128:
+    // row i of the interleaved product only adds a_i*a_i and a_i * 2*(a div 2^(32(i+1))) (the pairs j < i were added, doubled, in
+    // row j), i.e. the two carry chains lose their first ceil(i/2) / floor(i/2) pairs.  The doubled upper part's limbs are those
+    // of d = 2a, except its lowest one (j = i + 1), which must not carry the bit shifted out of a_i: e_j = (a_j << 1) mod 2^32.  The running limb that fixes m in row i
+    // only depends on pairs of total weight <= i, all of which have been added by then, so every m - and therefore the
+    // result - equals the full product's.  2a < 4m < 2^256 fits eight limbs, and a_i * 2a + m * p < 2^288 keeps the nine-limb
+    // accumulators from overflowing.
+    __device__ __forceinline__ static Fp sqr_lazy(const Fp& a) {
+#ifndef __CUDA_ARCH__
+        return a.normalized() * a.normalized();
+#else
+        uint32_t d[8];   // 2a
+        asm("add.cc.u32 %0, %8, %8;\n\t"
+            "addc.cc.u32 %1, %9, %9;\n\t"
+            "addc.cc.u32 %2, %10, %10;\n\t"
+            "addc.cc.u32 %3, %11, %11;\n\t"
+            "addc.cc.u32 %4, %12, %12;\n\t"
+            "addc.cc.u32 %5, %13, %13;\n\t"
+            "addc.cc.u32 %6, %14, %14;\n\t"
+            "addc.u32 %7, %15, %15;"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]), "=r"(d[4]), "=r"(d[5]), "=r"(d[6]), "=r"(d[7])
+            : "r"(a.l[0]), "r"(a.l[1]), "r"(a.l[2]), "r"(a.l[3]), "r"(a.l[4]), "r"(a.l[5]), "r"(a.l[6]), "r"(a.l[7]));
+        uint32_t e[8];   // e_j = 2 a_j mod 2^32 (d_j without the carry from limb j - 1)
+#pragma unroll
+        for (int j = 1; j < 8; j++) e[j] = a.l[j] << 1;
+        uint32_t A[9], B[9], nA[9], nB[9], m;
+#define ZKW_SQR_REDUCE(AA, BB)                                               \
+        m = AA[0] * P::INV;                                                  \
+        mad_pairs(AA, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);        \
+        mad_pairs(BB, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+#define ZKW_SQR_NEXT()                                                       \
+        _Pragma("unroll") for (int k = 0; k < 9; k++) { A[k] = nA[k]; B[k] = nB[k]; }
+#define ZKW_SQR_COPY_B()                                                     \
+        _Pragma("unroll") for (int k = 1; k < 9; k++) nA[k] = B[k];
+        // row 0: a0*a0, a0*e1, a0*d2 .. a0*d7
+        mul_pairs(A, a.l[0], d[2], d[4], d[6], a.l[0]);
+        mul_pairs(B, e[1], d[3], d[5], d[7], a.l[0]);
+        ZKW_SQR_REDUCE(A, B)
+        // row 1: odd chain a1*a1, d3, d5, d7; even chain d2, d4, d6 (pair 0 absent)
+        shift_mad_pairs(nA[0], nB, B[0], A, a.l[1], d[3], d[5], d[7], a.l[1]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s1(nA, e[2], d[4], d[6], a.l[1]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 2: odd chain d3, d5, d7 (pair 0 absent); even chain a2*a2, d4, d6
+        shift_mad_pairs_s1(nA[0], nB, B[0], A, e[3], d[5], d[7], a.l[2]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s1(nA, a.l[2], d[4], d[6], a.l[2]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 3: odd chain a3*a3, d5, d7; even chain d4, d6
+        shift_mad_pairs_s1(nA[0], nB, B[0], A, a.l[3], d[5], d[7], a.l[3]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s2(nA, e[4], d[6], a.l[3]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 4: odd chain d5, d7; even chain a4*a4, d6
+        shift_mad_pairs_s2(nA[0], nB, B[0], A, e[5], d[7], a.l[4]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s2(nA, a.l[4], d[6], a.l[4]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 5: odd chain a5*a5, d7; even chain d6
+        shift_mad_pairs_s2(nA[0], nB, B[0], A, a.l[5], d[7], a.l[5]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s3(nA, e[6], a.l[5]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 6: odd chain d7; even chain a6*a6
+        shift_mad_pairs_s3(nA[0], nB, B[0], A, e[7], a.l[6]);
+        ZKW_SQR_COPY_B()
+        mad_pairs_s3(nA, a.l[6], a.l[6]);
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+        // row 7: odd chain a7*a7; even chain empty
+        shift_mad_pairs_s3(nA[0], nB, B[0], A, a.l[7], a.l[7]);
+        ZKW_SQR_COPY_B()
+        ZKW_SQR_REDUCE(nA, nB)
+        ZKW_SQR_NEXT()
+#undef ZKW_SQR_REDUCE
+#undef ZKW_SQR_NEXT
+#undef ZKW_SQR_COPY_B
         Fp r;
         asm("add.cc.u32 %0, %8, %16;\n\t"
             "addc.cc.u32 %1, %9, %17;\n\t"

@@ -51,7 +51,7 @@ EXPORTS = [
     "zkw_ecdsa_circuit_permutation", "zkw_ecdsa_synthesize",
     "zkw_pk_write", "zkw_pk_read", "zkw_vk_write", "zkw_vk_read",
     "zkw_prover_create", "zkw_prover_destroy", "zkw_prover_ctx", "zkw_prover_pk", "zkw_prover_last_synthesis_ms", "zkw_prover_prove",
-    "zkw_prove_batch", "zkw_g1_sum",
+    "zkw_prove_batch", "zkw_g1_sum", "zkw_selftest_field",
 ]
 
 
@@ -135,6 +135,7 @@ def load_library() -> C.CDLL:
     lib.zkw_profile_read.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.zkw_profile_names.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     lib.zkw_profile_filter.argtypes = [C.c_void_p, C.c_char_p]
+    lib.zkw_selftest_field.argtypes = [C.c_void_p, C.c_uint64, C.c_uint, C.POINTER(C.c_uint)]
     lib.zkw_synth_witness.argtypes = [C.POINTER(CircuitShape), C.c_uint32, C.c_char_p, C.c_size_t, C.POINTER(u64p), C.POINTER(C.c_size_t)]
     lib.zkw_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
     lib.zkw_host_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -290,6 +291,12 @@ class Context:
     # -- per-kernel device timing ------------------------------------------------------------------
     def profile_enable(self, on: bool = True):
         self._check(self.lib.zkw_profile_enable(self.h, int(on)), "zkw_profile_enable")
+
+    def selftest_field(self, seed: int = 1, count: int = 1 << 16) -> tuple[int, int]:
+        """(Fr mismatches, Fq mismatches) of the dedicated squaring against the general product on the device"""
+        out = (C.c_uint * 2)()
+        self._check(self.lib.zkw_selftest_field(self.h, C.c_uint64(seed), C.c_uint(count), out), "zkw_selftest_field")
+        return int(out[0]), int(out[1])
 
     def profile_filter(self, kernel: str | None):
         """time only launches of `kernel` (None: all kernels)"""
