@@ -85,6 +85,23 @@ def test_device_prover_matches_oracle_prover_bit_for_bit(zkw, oracle, degree, A,
         ctx.close()
 
 
+def test_lookup_rank_binary_search_path(zkw, oracle, monkeypatch):
+    """lookup_rank_kernel probes table[v] first (range tables hold 0 .. T-1 in order); with the probe switched off every rank
+    comes from the binary search - the proof bytes must not change."""
+    from oracle import halo2_ref as h
+    ctx = zkw.Context(0)
+    try:
+        params = zkw.CircuitParams("Simple", 7, 2, 1, 1, 6, 88, 3)
+        circ, shape, oshape, pk, fixed_c, mapping = _setup(zkw, oracle, ctx, params)
+        adv = [oracle.fr_to_mont([int(x) for x in col]) for col in circ.synthesize(b"probe")]
+        want = zkw.create_proof(ctx, pk, adv, seed=3, transcript=zkw.TRANSCRIPT_EVM)
+        monkeypatch.setenv("ZKW_LOOKUP_NO_PROBE", "1")
+        assert zkw.create_proof(ctx, pk, adv, seed=3, transcript=zkw.TRANSCRIPT_EVM) == want
+        pk.close()
+    finally:
+        ctx.close()
+
+
 def test_device_prover_rejects_lookup_input_outside_table(zkw, oracle):
     ctx = zkw.Context(0)
     try:

@@ -728,6 +728,7 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     // ---- 0. witness-independent work first: the vanishing argument's random polynomial and its commitment (absorbed by
     // the transcript after the grand products).  With zkw_create_proof_overlapped the caller is still synthesising the
     // witness on the host while this MSM runs; `ready` blocks until the advice columns may be read.
+    const int lookup_probe = getenv("ZKW_LOOKUP_NO_PROBE") ? 0 : 1;   // test knob: force the binary search of lookup_rank_kernel
     LanePipe pipe(ctx, tr, n);
     uint64_t* random_poly;
     int t_random;
@@ -791,7 +792,7 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
             }
             ZKW_TRY(sc.get(vb, (void**)&lk_a[l])); ZKW_TRY(sc.get(vb, (void**)&lk_s[l])); ZKW_TRY(sc.get(vb, (void**)&lk_z[l]));
             ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (m + 1) * 4, st));
-            { ProfScope ps_(ctx, "lookup_rank_kernel"); lookup_rank_kernel<<<grid_for(u, 128), 128, 0, st>>>((const uint4*)lk_inp[l], (const uint4*)pk->table_canon, m, rank, counts, err, u); }
+            { ProfScope ps_(ctx, "lookup_rank_kernel"); lookup_rank_kernel<<<grid_for(u, 128), 128, 0, st>>>((const uint4*)lk_inp[l], (const uint4*)pk->table_canon, m, rank, counts, err, u, lookup_probe); }
             ZKW_LAUNCHED(ctx);
             { ProfScope ps_(ctx, "lookup_scan_kernel"); lookup_scan_kernel<<<1, 1024, 0, st>>>(counts, pk->table_mult, m, run_start, rep_start, desc_start, err); }
             ZKW_LAUNCHED(ctx);

@@ -270,11 +270,19 @@ __device__ __forceinline__ int cmp256(const Fr& a, const Fr& b) {
 
 // rank[i] = index of input value i in the sorted distinct table (canonical form); histogram of ranks
 __global__ void lookup_rank_kernel(const uint4* inp, const uint4* table_sorted_canon, uint32_t m, uint32_t* rank, uint32_t* counts,
-                                   uint32_t* error_flag, size_t u) {
+                                   uint32_t* error_flag, size_t u, int probe) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= u) return;
     const Fr v = Fr::load(inp + 2 * i).from_mont();
     uint32_t lo = 0, hi = m;  // first index with table[idx] >= v
+    // range tables hold 0 .. T-1 in order, so a value below m is (almost always) its own rank: one probe instead of log2(m)
+    // dependent loads; anything else takes the binary search
+    if (probe && !(v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) && v.l[0] < m &&
+        cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)v.l[0]), v) == 0) {
+        rank[i] = v.l[0];
+        atomicAdd(&counts[v.l[0]], 1u);
+        return;
+    }
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         if (cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)mid), v) < 0) lo = mid + 1; else hi = mid;
@@ -304,27 +312,36 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
 
 __global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m, uint32_t* run_start,
                                                            uint32_t* rep_start, uint32_t* desc_start, uint32_t* error_flag) {
+    // four consecutive entries per thread and tile (4096 per tile): a quarter of the barrier-separated iterations of the
+    // one-entry-per-thread form - this kernel sits alone on the proof's critical path between the lookup ranks and A' / S'
     __shared__ uint32_t wsum[3][32];
     __shared__ uint32_t carry[3];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t < 3) carry[t] = 0;
     __syncthreads();
-    for (uint32_t base = 0; base < m; base += 1024) {
-        const uint32_t j = base + t;
-        uint32_t q[3] = {0, 0, 0};
-        if (j < m) {
-            const uint32_t cj = counts[j];
-            q[0] = cj;
-            q[1] = cj ? cj - 1 : 0;
-            const uint32_t jj = m - 1 - j;
-            const uint32_t cjj = counts[jj], mu = mult[jj];
-            if (cjj && mu == 0) atomicExch(error_flag, 1u);
-            q[2] = mu - (cjj ? 1u : 0u);
+    for (uint32_t base = 0; base < m; base += 4096) {
+        uint32_t q[3][4];
+        uint32_t tot[3] = {0, 0, 0};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const uint32_t j = base + 4 * (uint32_t)t + e;
+            q[0][e] = q[1][e] = q[2][e] = 0;
+            if (j < m) {
+                const uint32_t cj = counts[j];
+                q[0][e] = cj;
+                q[1][e] = cj ? cj - 1 : 0;
+                const uint32_t jj = m - 1 - j;
+                const uint32_t cjj = counts[jj], mu = mult[jj];
+                if (cjj && mu == 0) atomicExch(error_flag, 1u);
+                q[2][e] = mu - (cjj ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) tot[k] += q[k][e];
         }
         uint32_t inc[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            inc[k] = warp_incl_scan_u32(q[k], lane);
+            inc[k] = warp_incl_scan_u32(tot[k], lane);
             if (lane == 31) wsum[k][warp] = inc[k];
         }
         __syncthreads();
@@ -333,10 +350,15 @@ __global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* count
             for (int k = 0; k < 3; k++) wsum[k][lane] = warp_incl_scan_u32(wsum[k][lane], lane);
         }
         __syncthreads();
-        if (j < m) {
-            uint32_t* outs[3] = {run_start, rep_start, desc_start};
+        uint32_t* outs[3] = {run_start, rep_start, desc_start};
 #pragma unroll
-            for (int k = 0; k < 3; k++) outs[k][j] = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - q[k];
+        for (int k = 0; k < 3; k++) {
+            uint32_t run = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - tot[k];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t j = base + 4 * (uint32_t)t + e;
+                if (j < m) { outs[k][j] = run; run += q[k][e]; }
+            }
         }
         __syncthreads();
         if (t < 3) carry[t] += wsum[t][31];
