@@ -16,6 +16,7 @@ import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 TAU = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
 
@@ -219,6 +220,53 @@ def test_key_files_round_trip(zkw, oracle, tmp_path):
     finally:
         zkw.prover._STATES.pop((15, pk_path, 0), None)
         st.close()
+
+
+def test_request_path_from_plain_c(zkw, oracle, tmp_path):
+    """tests/host/ffi_prover.c: download_keys + generate_proof_evm + a concurrent batch driven from plain C11 through the C ABI
+    alone (pedantic gcc, no Python in the proving process): key files written and re-read, single proofs with fixed seeds (the
+    same bytes the Python mirror produces), a forged assertion refused with ZKW_ERR_SIGNATURE, an OS-seeded batch over two
+    provers - every proof accepted by the oracle verifier under the key read back from the verifying-key FILE."""
+    import shutil
+    import struct
+    import subprocess
+    from oracle import halo2_ref as h
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    libdir = os.path.join(ROOT, "webauthn-halo2_b200")
+    exe = str(tmp_path / "ffi_prover")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-O1", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "host", "ffi_prover.c"), "-L", libdir, "-l:libzkw_b200.so", "-Wl,-rpath," + libdir],
+                   check=True, capture_output=True)
+    P = zkw.CircuitParams.for_degree(16)
+    assertions = [_assertion(300 + i)[1] for i in range(5)]
+    forged = assertions[2][:128] + bytes([assertions[2][128] ^ 1]) + assertions[2][129:]
+    blob = b"".join(assertions[:2] + [forged] + assertions[3:])
+    (tmp_path / "a.bin").write_bytes(blob)
+    pk_path, vk_path, out_path = str(tmp_path / "pk.bin"), str(tmp_path / "vk.bin"), str(tmp_path / "proofs.bin")
+    res = subprocess.run([exe, str(P.degree), str(P.num_advice), str(P.num_lookup_advice), str(P.num_fixed), str(P.lookup_bits), str(P.limb_bits),
+                          pk_path, vk_path, str(tmp_path / "a.bin"), out_path], capture_output=True, text=True)
+    assert res.returncode == 0 and "FFI_PROVER OK count=5" in res.stdout, res.stdout + res.stderr
+    shape, fx, pm, dg, _ = zkw.prover.read_vk(vk_path)
+    vk = h.VerifyingKey(h.Shape(16, 8, 2, 1), [oracle.g1_affine_to_ints(p) for p in fx], [oracle.g1_affine_to_ints(p) for p in pm],
+                        oracle.fr_from_mont(dg.reshape(1, 4))[0])
+    tau = 0x3d6c6d4b1b3c5a8e
+    raw = open(out_path, "rb").read()
+    pos, records = 0, []
+    while pos < len(raw):
+        status, length = struct.unpack_from("<II", raw, pos)
+        records.append((status - (1 << 32) if status >= 1 << 31 else status, raw[pos + 8: pos + 8 + length]))
+        pos += 8 + length
+    assert len(records) == 10
+    single, batch = records[:5], records[5:]
+    for i, (status, proof) in enumerate(single + batch):
+        if i % 5 == 2:
+            assert status == -7 and proof == b""                      # ZKW_ERR_SIGNATURE: nothing proven
+        else:
+            assert status == 0 and len(proof) > 1000
+            assert h.verify_proof(vk, proof, "evm", tau=tau), i
+    assert "batch_rc=-7" in res.stdout                                  # the batch reports its first error and proves the rest
+    assert all(single[i][1] != batch[i][1] for i in (0, 1, 3, 4))       # OS-seeded blinding differs from the fixed seeds
 
 
 def test_prover_pool_batch(zkw, oracle):
