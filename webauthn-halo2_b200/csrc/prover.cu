@@ -734,7 +734,12 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     int t_random;
     ZKW_TRY(sc.get(vb, (void**)&random_poly));
     ZKW_TRY(rand_fill(ctx, random_poly, n, seed, 4000, 0));
-    ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
+    // Its MSM is a full one-wave accumulation: whatever is queued on the other lanes while it is resident waits for it
+    // (a lane's one-CTA scan cannot get a slot).  When the witness is still being synthesised that is free time and the MSM
+    // goes first; when the advice is already here it is submitted after the (light) advice and permuted-lookup commitments,
+    // which the transcript needs first.
+    const bool random_first = ready != nullptr;
+    if (random_first) ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
     if (ready) ZKW_TRY(ready(ready_user));
 
     // ---- 1. advice ----
@@ -814,6 +819,7 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
             t_lk.push_back(ta); t_lk.push_back(ts);
         }
     }
+    if (!random_first) ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
     for (int t : t_adv) ZKW_TRY(pipe.write(t));
     const Fr theta = tr.squeeze();
     (void)theta;
