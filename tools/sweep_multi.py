@@ -1,6 +1,7 @@
 """BASELINE.json configs[4], multi-GPU leg: ONE BN254 G1 MSM of 2^k points split across the ranks of a
 torchrun job: every rank keeps the window tables of its contiguous slice of the SRS
-resident, reduces its slice to one point, the 96-byte partial results are all-gathered over NCCL and folded.
+resident, reduces its slice to one point, the 96-byte partial results are all-gathered over NCCL and folded on the host
+(multi_gpu._gather_and_fold, the code path of multi_gpu.SplitMsm and of bench.py's split_msm leg).
 Timed end to end (device MSM + collective + fold), max over ranks; the split result is checked against a
 single-GPU MSM over the whole SRS.  NTTs are not sharded (every size of the sweep fits one GPU): N GPUs run N
 independent transforms, so their aggregate rate is N x the single-GPU figure of tools/sweep.py.
@@ -45,19 +46,11 @@ def main():
         gen = torch.Generator(device=dev); gen.manual_seed(1000 + k)   # same scalars on every rank
         s = torch.randint(0, 1 << 62, (n, 4), dtype=torch.int64, device=dev, generator=gen); s[:, 3] &= (1 << 60) - 1
         mine = s[lo:hi].contiguous()
-        ones = np.tile(mg._FR_ONE_MONT, (world, 1))
 
         def split_once():
+            # the product path: per-rank MSM over resident window tables, NCCL all-gather of world x 96 bytes, host fold
             part = ctx.msm_dev(mine, hi - lo, zkw.BASES_G)
-            if world == 1:
-                return part
-            t = torch.from_numpy(part.view(np.int64).copy()).to(dev)
-            gathered = [torch.empty_like(t) for _ in range(world)]
-            dist.all_gather(gathered, t)
-            parts = np.stack([x.cpu().numpy().view(np.uint64) for x in gathered])
-            pts = parts[:, :8].copy()
-            pts[~parts[:, 8:].any(axis=1)] = 0
-            return ctx.msm(ones, pts)
+            return mg._gather_and_fold(part, world, dist if world > 1 else None, dev)
 
         res = split_once()
         ts = []
