@@ -271,9 +271,10 @@ int zkw_create_proof_overlapped(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* 
                                 const uint8_t seed[32], int transcript, unsigned flags, zkw_advice_ready_fn ready, void* user,
                                 uint8_t* out, size_t out_cap, size_t* out_len);
 
-/* Host-side witness synthesis for the shape-identical synthetic ECDSA circuit (stands in for
- * ECDSACircuit::synthesize, halo2-circuits/src/ecc/ecdsa_p256.rs:117-206, whose halo2-ecc chips are un-vendored):
- * fills cols_out[c] (c < num_advice: 4 * floor((2^k - blinding_factors - 1) / 4) cells; lookup-advice columns:
+/* TEST SHAPE ONLY (the real circuit is zkw_ecdsa_* below): host-side assignment of a PRNG-filled system with the same
+ * gate, lookup and copy-constraint kinds and the column counts of a config line - used for sizes the ECDSA circuit cannot
+ * fit (k < 11) and for byte-for-byte comparisons with the Python oracle prover; it attests nothing about a signature.
+ * Fills cols_out[c] (c < num_advice: 4 * floor((2^k - blinding_factors - 1) / 4) cells; lookup-advice columns:
  * 2^k - blinding_factors - 1 cells) with canonical values < 2^64 keyed by the assertion bytes, and rows_out[c]
  * (may be NULL) with the cell counts.  Pure host code: no device, no context.  Feed the columns to
  * zkw_create_proof_ex with ZKW_ADVICE_U64. */
