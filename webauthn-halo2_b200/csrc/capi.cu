@@ -120,7 +120,7 @@ static void profile_collect(zkw_ctx* ctx) {
     if (ctx->prof_pending.empty()) return;
     cudaStreamSynchronize(ctx->stream);
     for (int i = 1; i < zkw_ctx::kMsmLanes; i++) if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
-    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    for (int i = 0; i < zkw_ctx::kAuxStreams; i++) if (ctx->aux_stream[i]) cudaStreamSynchronize(ctx->aux_stream[i]);
     // ZKW_TIMELINE=<file>: also append one "name,stream,start_ms,duration_ms" line per launch (start relative
     // to the first launch profiled), which is enough to see what overlaps what without a system profiler
     const char* tl_path = getenv("ZKW_TIMELINE");
@@ -288,16 +288,19 @@ void zkw_ctx_destroy(zkw_ctx* ctx) {
     // drain every stream of the context (an early error return may have left work queued on the aux stream or the
     // lanes) and read the timing events back while the streams they were recorded on still exist
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
+    for (int i = 0; i < zkw_ctx::kAuxStreams; i++) if (ctx->aux_stream[i]) cudaStreamSynchronize(ctx->aux_stream[i]);
     for (int i = 0; i < zkw_ctx::kMsmLanes; i++)
         if (ctx->lane_stream[i]) cudaStreamSynchronize(ctx->lane_stream[i]);
     profile_collect(ctx);
     for (auto& kv : ctx->twiddles) free_buffer(kv.second);
     for (auto& kv : ctx->staged_twiddles) free_buffer(kv.second);
-    free_buffer(ctx->ntt_scratch); free_buffer(ctx->ntt_scratch_aux); free_buffer(ctx->msm_ws);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    free_buffer(ctx->ntt_scratch); free_buffer(ctx->msm_ws);
+    for (int i = 0; i < zkw_ctx::kAuxStreams; i++) {
+        free_buffer(ctx->ntt_scratch_aux[i]);
+        if (ctx->aux_stream[i]) cudaStreamDestroy(ctx->aux_stream[i]);
+        if (ctx->aux_join[i]) cudaEventDestroy(ctx->aux_join[i]);
+    }
     if (ctx->aux_fork) cudaEventDestroy(ctx->aux_fork);
-    if (ctx->aux_join) cudaEventDestroy(ctx->aux_join);
     free_buffer(ctx->io_a); free_buffer(ctx->io_b); free_buffer(ctx->io_c); free_buffer(ctx->ptr_table); free_buffer(ctx->arena);
     msm_free_basis(ctx->bases[0]); msm_free_basis(ctx->bases[1]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

@@ -67,9 +67,13 @@ struct zkw_ctx {
     // per-(omega, log_n, pass) compact copies of a pass's last-stage twiddles, laid out for one bulk copy per tile
     std::map<zkw::StagedTwiddleKey, zkw::DeviceBuffer> staged_twiddles;
     // reusable scratch areas (grown on demand, never shrunk)
-    zkw::DeviceBuffer ntt_scratch, ntt_scratch_aux;
-    cudaStream_t aux_stream = nullptr;   // prover: transforms that overlap the main stream's MSMs
-    cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
+    // prover: transforms that overlap the main stream's MSMs run on an auxiliary stream (up to three, round robin, with
+    // ZKW_AUX_STREAMS: measured, no gain — prover.cu create_proof_impl)
+    static constexpr int kAuxStreams = 3;
+    zkw::DeviceBuffer ntt_scratch, ntt_scratch_aux[kAuxStreams];
+    cudaStream_t aux_stream[kAuxStreams] = {nullptr};
+    cudaEvent_t aux_fork = nullptr, aux_join[kAuxStreams] = {nullptr};
+    int aux_count = 0, aux_next = 0;     // streams in use (ZKW_AUX_STREAMS, default 1) and the round-robin cursor
     zkw::DeviceBuffer msm_ws;
     // MSM lanes: lane 0 runs on `stream`; lanes 1.. own a side stream so that the latency-bound tails of
     // one MSM overlap the accumulation of the next (msm_run_batch)

@@ -337,7 +337,9 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
     // work on the auxiliary stream gets its own scratch so that it may overlap main-stream transforms
     const bool aux = stream && stream != ctx->stream;
     cudaStream_t st = stream ? stream : ctx->stream;
-    DeviceBuffer& scratch = aux ? ctx->ntt_scratch_aux : ctx->ntt_scratch;
+    int aux_i = 0;
+    for (int i = 1; i < zkw_ctx::kAuxStreams; i++) if (stream && stream == ctx->aux_stream[i]) aux_i = i;
+    DeviceBuffer& scratch = aux ? ctx->ntt_scratch_aux[aux_i] : ctx->ntt_scratch;
     if (log_n > 28 || src_log_n > log_n) return ZKW_ERR_INVALID;
     const size_t n = (size_t)1 << log_n;
     if (log_n == 0) {
