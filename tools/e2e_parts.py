@@ -1,8 +1,9 @@
-import importlib, sys, time, ctypes as C
+"""Where a generate_proof_evm call spends its time (development aid):  python tools/e2e_parts.py [degree]"""
+import importlib, os, sys, time
 sys.path.insert(0, ".")
 import numpy as np, torch
 zkw = importlib.import_module("webauthn-halo2_b200")
-st = zkw.ProverState(zkw.CircuitParams.for_degree(19), 0)
+st = zkw.ProverState(zkw.CircuitParams.for_degree(int(sys.argv[1]) if len(sys.argv) > 1 else 19), 0)
 a = [zkw.synthetic_assertion(i) for i in range(6)]
 for i in range(3): st.prove(a[i], zkw.TRANSCRIPT_EVM, seed=i)
 # (1) e2e
@@ -27,4 +28,4 @@ h2d=(time.perf_counter()-t0)/10*1e3
 t0=time.perf_counter()
 for i in range(10): st.circuit.synthesize(*[a[i%6][32*j:32*j+32] for j in range(5)], out=stg)
 syn=(time.perf_counter()-t0)/10*1e3
-print(f"e2e {e2e:.2f} ms | resident {res:.2f} | pinned-host columns (H2D inside) {h2d:.2f} | synthesis alone {syn:.2f}")
+print(f"k={sys.argv[1] if len(sys.argv) > 1 else 19} threads={os.environ.get('ZKW_SYNTH_THREADS', 'default')} e2e {e2e:.2f} ms | resident {res:.2f} | pinned-host columns (H2D inside) {h2d:.2f} | synthesis alone {syn:.2f}")

@@ -24,6 +24,9 @@
 // arithmetic; tests compare every cell, selector and permutation entry with oracle/ecdsa_circuit.py.
 #include <cstdint>
 #include <cstring>
+#include <ctime>
+#include <chrono>
+#include <cstdio>
 #include <algorithm>
 #include <cstdlib>
 #include <thread>
@@ -313,7 +316,7 @@ struct Structure {   // what keygen needs; filled by the structure pass
     struct Checkpoint {
         std::vector<uint64_t> rows;
         uint32_t acc_ids[8], facc_ids[8];   // x limbs 0-2, x native, y limbs 0-2, y native
-        uint64_t cells_before;
+        uint64_t cells_before, lookups_before;
     };
     std::vector<Checkpoint> checkpoints;
 };
@@ -392,10 +395,17 @@ struct Builder {
     }
     void end() { rows[cur_col] = cur_row0 + cur_len; }
 
+    uint64_t lk_cursor = 0;           // lookup cells so far (lookup-column mode): cell i -> column A + i mod L, row i div L
     void lookup(uint32_t cell) {
-        if (!st) return;
-        if (selector_mode) st->q_lookup[cell & (n - 1)] = 1;
-        else st->lookups.push_back(cell);
+        if (selector_mode) {
+            if (st) st->q_lookup[cell & (n - 1)] = 1;
+            return;
+        }
+        // the witness pass copies the value into its lookup column now, while the cell is still in cache (a gather over the
+        // finished columns afterwards costs a third of a millisecond, serial)
+        const uint64_t i = lk_cursor++;
+        if (st) st->lookups.push_back(cell);
+        else if (L && i / L < u) memcpy(adv[A + i % L] + 4 * (i / L), at(cell), 32);
     }
     void equal(uint32_t a, uint32_t b) {
         if (st) st->copies.emplace_back(a, b);
@@ -1229,6 +1239,7 @@ struct Builder {
                 ids_of(facc, cp.facc_ids);
                 cp.cells_before = 0;
                 for (uint64_t r : rows) cp.cells_before += r;
+                cp.lookups_before = lk_cursor;
                 if (st->checkpoints.size() <= sgm) st->checkpoints.resize(sgm + 1);
                 st->checkpoints[sgm] = cp;
             }
@@ -1305,12 +1316,14 @@ void setup_builder(Builder& b, const zkw_ecdsa_circuit* c) {
     b.init_mod(b.mc_n, moduli().fn);
 }
 
-// worker threads of one synthesis: ZKW_SYNTH_THREADS, default min(4, hardware threads / 2)
+// worker threads of one synthesis: ZKW_SYNTH_THREADS, default min(8, hardware threads / 2).  Measured on the GPU box's 16-core
+// host (ZKW_SYNTH_TIMING=1, tools/synth_timing.py): 0.57 ms serial (denominator pre-pass 0.32, prologue 0.25) + 3.0 ms / threads
+// + ~0.2 ms of thread start/join: 3.9 ms with one thread, 1.6-1.9 with four, 1.25-1.4 with eight.
 unsigned synth_threads() {
     const char* e = getenv("ZKW_SYNTH_THREADS");
     if (e && atoi(e) > 0) return (unsigned)std::min(atoi(e), 16);
     static const unsigned hw = std::thread::hardware_concurrency();
-    return std::max(1u, std::min(4u, hw / 2));
+    return std::max(1u, std::min(8u, hw / 2));
 }
 
 U256 load_le(const uint8_t b[32]) {
@@ -1475,7 +1488,11 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
                                     int* signature_ok) {
     if (!c || !c->fits || !pubkey_x || !pubkey_y || !r || !s || !msg_hash || !advice_out) return ZKW_ERR_INVALID;
     Builder b;
+    auto T0 = std::chrono::steady_clock::now();
+    const bool timing = getenv("ZKW_SYNTH_TIMING") != nullptr;   // development aid: phase and per-thread times on stderr
+    auto lap = [&](const char* what) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "  %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - T0).count()); T0 = t; } };
     setup_builder(b, c);
+    lap("setup");
     for (unsigned i = 0; i < b.A + b.L; i++) {
         if (!advice_out[i]) return ZKW_ERR_INVALID;
         b.adv.push_back(advice_out[i]);
@@ -1483,6 +1500,7 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
     bool ok = false;
     const U256 vx = load_le(pubkey_x), vy = load_le(pubkey_y), vr = load_le(r), vs = load_le(s), vm = load_le(msg_hash);
     const bool have_traj = b.precompute_denominators(vx, vy, vr, vs, vm);
+    lap("denominators");
     const unsigned nthreads = have_traj ? synth_threads() : 1;
     if (nthreads <= 1 || c->st.checkpoints.empty()) {
         b.run(vx, vy, vr, vs, vm, &ok);
@@ -1495,6 +1513,7 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
         Builder::RunCtx rc;
         Builder::EPt acc, facc;
         b.prologue(vx, vy, vr, vs, vm, rc, acc, facc);
+        lap("prologue");
         const unsigned nseg = b.num_segments(rc.nw), nw = rc.nw;
         const auto& cps = c->st.checkpoints;
         if (cps.size() != nseg) return ZKW_ERR_STATE;
@@ -1518,6 +1537,7 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
             if (s0 >= s1) return;
             const auto& cp = cps[s0];
             w.rows = cp.rows;
+            w.lk_cursor = cp.lookups_before;
             w.dinv_next = Builder::first_op_of(s0, nw);
             Builder::EPt a2 = acc, f2 = facc;
             if (t > 0) {
@@ -1532,13 +1552,18 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
                 }
             }
             bool okt = true;
+            timespec ts0, ts1;
+            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts0);
             w.run_segments(rc, s0, s1, a2, f2, &okt);
+            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts1);
+            if (timing) fprintf(stderr, "    thread %u segments [%u,%u) cells %llu cpu %.3f ms\n", t, s0, s1, (unsigned long long)((s1 < nseg ? cps[s1].cells_before : total) - cp.cells_before), (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
             if (s1 == nseg) done_ok[t] = okt ? 1 : 2;
         };
         std::vector<std::thread> threads;
         for (unsigned t = 1; t < nthreads; t++) threads.emplace_back(body, t);
         body(0);
         for (auto& th : threads) th.join();
+        lap("segments");
         for (unsigned t = 0; t < nthreads; t++) {
             if (workers[t].overflow) return ZKW_ERR_UNSUPPORTED;
             if (done_ok[t]) ok = done_ok[t] == 1;
@@ -1547,10 +1572,7 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
         }
         b.rows.assign(c->st.rows.begin(), c->st.rows.begin() + b.A);
     }
-    if (b.L) {
-        const std::vector<uint32_t>& lk = c->st.lookups;
-        for (size_t i = 0; i < lk.size(); i++) memcpy(b.adv[b.A + i % b.L] + 4 * (i / b.L), b.at(lk[i]), 32);
-    }
+    lap("lookup copy");
     if (rows_out)
         for (size_t i = 0; i < c->st.rows.size(); i++) rows_out[i] = (size_t)c->st.rows[i];
     if (signature_ok) *signature_ok = ok ? 1 : 0;
