@@ -197,9 +197,9 @@ static int host_transform(zkw_ctx* ctx, const uint64_t* src, size_t n_in, uint64
 
 // ---- device self-test of the hand-written field arithmetic variants -------------------------------------------------------
 // sqr_lazy(a) against mul_lazy(a, a) limb for limb, over the whole lazy range [0, 2m) of both fields: pseudo-random values plus
-// the corners 0, 1, m - 1, m, m + 1, 2m - 1.
+// the corners 0, 1, m - 1, m, m + 1, 2m - 1; mul2_lazy against two separate products.
 template <class F>
-__device__ bool selftest_sqr_one(uint64_t seed, unsigned i) {
+__device__ F selftest_value(uint64_t seed, unsigned i) {
     F a;
     uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1);
     for (int j = 0; j < 4; j++) {
@@ -224,9 +224,36 @@ __device__ bool selftest_sqr_one(uint64_t seed, unsigned i) {
         else if (i == 4) a = F::add_raw(F::add_raw(m1, one), one);      // m + 1
         else a = F::add_raw(F::add_raw(m1, m1), one);                   // 2m - 1
     }
+    return a;
+}
+template <class F>
+__device__ bool selftest_sqr_one(uint64_t seed, unsigned i) {
+    const F a = selftest_value<F>(seed, i);
     const F s = F::sqr_lazy(a), p = F::mul_lazy(a, a);
     bool ok = true;
     for (int j = 0; j < 8; j++) ok = ok && s.l[j] == p.l[j];
+    return ok;
+}
+// mul2_lazy(a, b, c, d) = a b + c d (one reduction for two products) against the two separate products, and neg_2m; the first
+// 6^2 indices pair the corner values with each other (2m - 1 four times is the bound's worst case), index 36 uses c = 2m (what
+// neg_2m returns for zero)
+template <class F>
+__device__ bool selftest_mul2_one(uint64_t seed, unsigned i) {
+    F a, b, c, d;
+    if (i < 36) {
+        a = selftest_value<F>(seed, i % 6); b = selftest_value<F>(seed, i / 6);
+        c = selftest_value<F>(seed, 5 - i % 6); d = selftest_value<F>(seed, i / 6);
+        if (i == 35) { a = b = c = d = selftest_value<F>(seed, 5); }
+    } else {
+        a = selftest_value<F>(seed, 4 * i); b = selftest_value<F>(seed, 4 * i + 1);
+        c = selftest_value<F>(seed, 4 * i + 2); d = selftest_value<F>(seed, 4 * i + 3);
+        if (i == 36) c = F::zero().neg_2m();
+    }
+    const F got = F::mul2_lazy(a, b, c, d).reduced_2m().normalized();
+    const F want = F::mul_lazy(a, b).normalized() + F::mul_lazy(c.reduced_2m(), d).normalized();
+    const F neg = F::add_raw(a, a.neg_2m()).reduced_2m().normalized();     // a + (2m - a) = 2m -> 0
+    bool ok = true;
+    for (int j = 0; j < 8; j++) ok = ok && got.l[j] == want.l[j] && neg.l[j] == 0;
     return ok;
 }
 __global__ void selftest_sqr_kernel(uint64_t seed, unsigned count, unsigned* mismatches) {
@@ -234,6 +261,8 @@ __global__ void selftest_sqr_kernel(uint64_t seed, unsigned count, unsigned* mis
     if (i >= count) return;
     if (!selftest_sqr_one<zkw::Fr>(seed, i)) atomicAdd(&mismatches[0], 1u);
     if (!selftest_sqr_one<zkw::Fq>(seed ^ 0x5555, i)) atomicAdd(&mismatches[1], 1u);
+    if (!selftest_mul2_one<zkw::Fr>(seed ^ 0x3333, i)) atomicAdd(&mismatches[0], 1u);
+    if (!selftest_mul2_one<zkw::Fq>(seed ^ 0x7777, i)) atomicAdd(&mismatches[1], 1u);
 }
 
 extern "C" {

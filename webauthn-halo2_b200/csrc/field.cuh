@@ -556,6 +556,72 @@ struct Fp {
         return r;
 #endif
     }
+    // (a * b + c * d) * R^-1 mod m for a, b, c, d <= 2m, with ONE interleaved reduction for the two products: 192 wide
+    // multiplies instead of 256.  T = a b + c d <= 8 m^2, so the result (T + M m) / R < m (8 m / R + 1) < 2.52 m for both BN254
+    // moduli (m / R < 0.19) - below 4m < 2^256, not below 2m: callers bring it back with reduced_2m().  The nine-limb
+    // accumulators take three row terms (< 2^257 each, halved by 2^32 per row) instead of two: still far below 2^288.
+    __device__ __forceinline__ static Fp mul2_lazy(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#ifndef __CUDA_ARCH__
+        return a.normalized() * b.normalized() + c.normalized() * d.normalized();
+#else
+        uint32_t A[9], B[9];
+        mul_pairs(A, a.l[0], a.l[2], a.l[4], a.l[6], b.l[0]);
+        mul_pairs(B, a.l[1], a.l[3], a.l[5], a.l[7], b.l[0]);
+        mad_pairs(A, c.l[0], c.l[2], c.l[4], c.l[6], d.l[0]);
+        mad_pairs(B, c.l[1], c.l[3], c.l[5], c.l[7], d.l[0]);
+        uint32_t m = A[0] * P::INV;
+        mad_pairs(A, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+        mad_pairs(B, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+#pragma unroll
+        for (int i = 1; i < 8; i++) {
+            uint32_t nA[9], nB[9];
+            shift_mad_pairs(nA[0], nB, B[0], A, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+#pragma unroll
+            for (int k = 1; k < 9; k++) nA[k] = B[k];
+            mad_pairs(nA, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
+            mad_pairs(nA, c.l[0], c.l[2], c.l[4], c.l[6], d.l[i]);
+            mad_pairs(nB, c.l[1], c.l[3], c.l[5], c.l[7], d.l[i]);
+            m = nA[0] * P::INV;
+            mad_pairs(nA, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
+            mad_pairs(nB, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
+#pragma unroll
+            for (int k = 0; k < 9; k++) { A[k] = nA[k]; B[k] = nB[k]; }
+        }
+        Fp r;
+        asm("add.cc.u32 %0, %8, %16;\n\t"
+            "addc.cc.u32 %1, %9, %17;\n\t"
+            "addc.cc.u32 %2, %10, %18;\n\t"
+            "addc.cc.u32 %3, %11, %19;\n\t"
+            "addc.cc.u32 %4, %12, %20;\n\t"
+            "addc.cc.u32 %5, %13, %21;\n\t"
+            "addc.cc.u32 %6, %14, %22;\n\t"
+            "addc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]), "r"(A[8]),
+              "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
+        return r;
+#endif
+    }
+    // 2m - a for a < 2m: -a in (0, 2m], one subtraction chain, no condition
+    __device__ __forceinline__ Fp neg_2m() const {
+#ifndef __CUDA_ARCH__
+        return normalized().neg();
+#else
+        Fp r;
+        asm("sub.cc.u32 %0, %8, %16;\n\t"
+            "subc.cc.u32 %1, %9, %17;\n\t"
+            "subc.cc.u32 %2, %10, %18;\n\t"
+            "subc.cc.u32 %3, %11, %19;\n\t"
+            "subc.cc.u32 %4, %12, %20;\n\t"
+            "subc.cc.u32 %5, %13, %21;\n\t"
+            "subc.cc.u32 %6, %14, %22;\n\t"
+            "subc.u32 %7, %15, %23;"
+            : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
+            : "r"(mod2(0)), "r"(mod2(1)), "r"(mod2(2)), "r"(mod2(3)), "r"(mod2(4)), "r"(mod2(5)), "r"(mod2(6)), "r"(mod2(7)),
+              "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7]));
+        return r;
+#endif
+    }
     // a + b for a, b < 2m; result < 2m
     __device__ __forceinline__ static Fp add_lazy(const Fp& a, const Fp& b) {
 #ifndef __CUDA_ARCH__
