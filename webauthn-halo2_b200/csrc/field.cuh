@@ -556,31 +556,41 @@ struct Fp {
         return r;
 #endif
     }
-    // (a * b + c * d) * R^-1 mod m for a, b, c, d <= 2m, with ONE interleaved reduction for the two products: 192 wide
-    // multiplies instead of 256.  T = a b + c d <= 8 m^2, so the result (T + M m) / R < m (8 m / R + 1) < 2.52 m for both BN254
-    // moduli (m / R < 0.19) - below 4m < 2^256, not below 2m: callers bring it back with reduced_2m().  The nine-limb
-    // accumulators take three row terms (< 2^257 each, halved by 2^32 per row) instead of two: still far below 2^288.
-    __device__ __forceinline__ static Fp mul2_lazy(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+    // sum_k a_k * b_k * R^-1 mod m with ONE interleaved reduction for the K products: 64 (K + 1) wide multiplies instead of
+    // 128 K.  T = sum a_k b_k, so the result (T + M m) / R < T / R + m; with m / R < 0.19 for both BN254 moduli:
+    //   K = 2, operands <= 2m:  < 2.52 m  (below 4m < 2^256: callers bring it back with reduced_2m())
+    //   K <= 5, operands <  m:  < 1.95 m  (the usual lazy range: normalized() makes it canonical)
+    // The nine-limb accumulators take K + 1 row terms (< 2^256 each, the sum divided by 2^32 per row): far below 2^288.
+    template <int K>
+    __device__ __forceinline__ static Fp dot_lazy(const Fp (&a)[K], const Fp (&b)[K]) {
 #ifndef __CUDA_ARCH__
-        return a.normalized() * b.normalized() + c.normalized() * d.normalized();
+        Fp r = zero();
+        for (int k = 0; k < K; k++) r = r + a[k].normalized() * b[k].normalized();
+        return r;
 #else
         uint32_t A[9], B[9];
-        mul_pairs(A, a.l[0], a.l[2], a.l[4], a.l[6], b.l[0]);
-        mul_pairs(B, a.l[1], a.l[3], a.l[5], a.l[7], b.l[0]);
-        mad_pairs(A, c.l[0], c.l[2], c.l[4], c.l[6], d.l[0]);
-        mad_pairs(B, c.l[1], c.l[3], c.l[5], c.l[7], d.l[0]);
+        mul_pairs(A, a[0].l[0], a[0].l[2], a[0].l[4], a[0].l[6], b[0].l[0]);
+        mul_pairs(B, a[0].l[1], a[0].l[3], a[0].l[5], a[0].l[7], b[0].l[0]);
+#pragma unroll
+        for (int k = 1; k < K; k++) {
+            mad_pairs(A, a[k].l[0], a[k].l[2], a[k].l[4], a[k].l[6], b[k].l[0]);
+            mad_pairs(B, a[k].l[1], a[k].l[3], a[k].l[5], a[k].l[7], b[k].l[0]);
+        }
         uint32_t m = A[0] * P::INV;
         mad_pairs(A, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
         mad_pairs(B, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
 #pragma unroll
         for (int i = 1; i < 8; i++) {
             uint32_t nA[9], nB[9];
-            shift_mad_pairs(nA[0], nB, B[0], A, a.l[1], a.l[3], a.l[5], a.l[7], b.l[i]);
+            shift_mad_pairs(nA[0], nB, B[0], A, a[0].l[1], a[0].l[3], a[0].l[5], a[0].l[7], b[0].l[i]);
 #pragma unroll
             for (int k = 1; k < 9; k++) nA[k] = B[k];
-            mad_pairs(nA, a.l[0], a.l[2], a.l[4], a.l[6], b.l[i]);
-            mad_pairs(nA, c.l[0], c.l[2], c.l[4], c.l[6], d.l[i]);
-            mad_pairs(nB, c.l[1], c.l[3], c.l[5], c.l[7], d.l[i]);
+            mad_pairs(nA, a[0].l[0], a[0].l[2], a[0].l[4], a[0].l[6], b[0].l[i]);
+#pragma unroll
+            for (int k = 1; k < K; k++) {
+                mad_pairs(nA, a[k].l[0], a[k].l[2], a[k].l[4], a[k].l[6], b[k].l[i]);
+                mad_pairs(nB, a[k].l[1], a[k].l[3], a[k].l[5], a[k].l[7], b[k].l[i]);
+            }
             m = nA[0] * P::INV;
             mad_pairs(nA, P::mod(0), P::mod(2), P::mod(4), P::mod(6), m);
             mad_pairs(nB, P::mod(1), P::mod(3), P::mod(5), P::mod(7), m);
@@ -601,6 +611,11 @@ struct Fp {
               "r"(B[0]), "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
         return r;
 #endif
+    }
+    // a b + c d for operands <= 2m: result < 2.52 m, see dot_lazy
+    __device__ __forceinline__ static Fp mul2_lazy(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        const Fp x[2] = {a, c}, y[2] = {b, d};
+        return dot_lazy<2>(x, y);
     }
     // 2m - a for a < 2m: -a in (0, 2m], one subtraction chain, no condition
     __device__ __forceinline__ Fp neg_2m() const {

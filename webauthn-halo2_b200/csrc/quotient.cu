@@ -129,16 +129,24 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs q) {
         if (q.L) inp = Fr::load_nc(q.advice[q.A + k] + 2 * idx);
         else inp = Fr::load_nc(q.q_lookup + 2 * idx) * Fr::load_nc(q.advice[0] + 2 * idx);
         const Fr tab = Fr::load_nc(q.table + 2 * idx);
-        acc0 = acc0 + weighted(q.one - z);
-        accl = accl + weighted(z.sqr() - z);
-        Fr lhs = (ap + beta) * (sp + gamma) * zn;
-        Fr rhs = (inp + beta) * (tab + gamma) * z;
-        acca = acca + weighted(lhs - rhs);
-        Fr ams = ap - sp;
-        acc0 = acc0 + weighted(ams);
-        acca = acca + weighted((ap - app) * ams);
+        // the five lookup constraints carry the weights y^e .. y^(e-4); the two l_0 terms and the two l_active terms are each
+        // folded as ONE two-product Montgomery pass (Fr::dot_lazy: one reduction per pair)
+        const Fr lhs = (ap + beta) * (sp + gamma) * zn;
+        const Fr rhs = (inp + beta) * (tab + gamma) * z;
+        const Fr ams = ap - sp;
+        {
+            const Fr g0[2] = {q.one - z, ams}, w0[2] = {Fr::load_nc(q.ypow + 2 * e), Fr::load_nc(q.ypow + 2 * (e - 3))};
+            acc0 = acc0 + Fr::dot_lazy<2>(g0, w0).normalized();
+            accl = accl + (z.sqr() - z) * Fr::load_nc(q.ypow + 2 * (e - 1));
+            const Fr ga[2] = {lhs - rhs, (ap - app) * ams}, wa[2] = {Fr::load_nc(q.ypow + 2 * (e - 2)), Fr::load_nc(q.ypow + 2 * (e - 4))};
+            acca = acca + Fr::dot_lazy<2>(ga, wa).normalized();
+            e -= 5;
+        }
     }
-    v = v * Fr::load_nc(q.ypow + 2 * q.rest_constraints) + acc0 * l0 + accl * ll + acca * la;
+    {   // h = gates * y^rest + acc0 l_0 + accl l_last + acca l_active: four products, one reduction
+        const Fr fa[4] = {v, acc0, accl, acca}, fb[4] = {Fr::load_nc(q.ypow + 2 * q.rest_constraints), l0, ll, la};
+        v = Fr::dot_lazy<4>(fa, fb).normalized();
+    }
     v = v * q.t_evals[idx & (q.rot_scale - 1)];
     v.store(q.h + 2 * idx);
 }
