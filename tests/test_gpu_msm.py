@@ -128,6 +128,29 @@ def test_msm_skewed_scalars_over_window_tables(zkw, oracle, kind):
         c.close()
 
 
+@pytest.mark.parametrize("binned", [0, 1])
+@pytest.mark.parametrize("n", [33, 1000, 4097, (1 << 14) + 7])
+def test_msm_both_entry_sorts(zkw, oracle, monkeypatch, binned, n):
+    """The bucket order of the entries comes from one of two sorts (msm.cu): the direct one (a global atomic per entry) and
+    the binned one (coarse bins, shared-memory counting, chunks staged by bulk copy).  Both are forced here on every size,
+    with uniform and with skewed scalars, over window tables and over caller bases."""
+    monkeypatch.setenv("ZKW_MSM_BINNED_SORT", str(binned))
+    monkeypatch.setenv("ZKW_MSM_BINNED_MIN_ENTRIES", "0")
+    g = _bases(oracle, n, 4000 + n)
+    rng = np.random.default_rng(n)
+    skew = [int(v) for v in rng.choice([0, 1, 1, 2, 3, (1 << 18) - 1, (1 << 88) - 1, 12345678901234567890], size=n)]
+    runs = [(i // 100) * 0x10001000100010001 + 7 for i in range(n)]          # constant stretches: whole warps agree on every digit
+    c = zkw.Context(0)
+    try:
+        c.srs_load(g, None)
+        for s in (oracle.fr_random(n, 4100 + n), oracle.fr_to_mont(skew), oracle.fr_to_mont(runs)):
+            want = _affine(oracle, oracle.best_multiexp(s, g))
+            assert np.array_equal(c.msm(s, which=zkw.BASES_G)[:8], want)
+            assert np.array_equal(c.msm(s, g)[:8], want)
+    finally:
+        c.close()
+
+
 def test_msm_before_srs_load_is_an_error(zkw, oracle):
     c = zkw.Context(0)
     try:

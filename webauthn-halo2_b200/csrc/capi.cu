@@ -307,6 +307,10 @@ int zkw_ctx_create(int device, zkw_ctx** out) {
     if (env) ctx->msm_window_bits = atoi(env);
     env = getenv("ZKW_MSM_PRECOMPUTE");
     if (env) ctx->msm_precompute = atoi(env);
+    env = getenv("ZKW_MSM_BINNED_SORT");
+    if (env) ctx->msm_binned_sort = atoi(env);
+    env = getenv("ZKW_MSM_BINNED_MIN_ENTRIES");
+    if (env) ctx->msm_binned_min_entries = atoi(env);
     *out = ctx;
     return ZKW_OK;
 }

@@ -59,6 +59,10 @@ struct zkw_ctx {
     // MSM tuning: window bits (0 = automatic) and whether fixed bases get window tables
     int msm_window_bits = 0;
     int msm_precompute = 1;
+    // bucket sort of the MSM entries: binned (shared-memory counting, msm.cu) unless ZKW_MSM_BINNED_SORT=0; MSMs with
+    // fewer entries than msm_binned_min_entries keep the direct three-kernel sort (fewer launches)
+    int msm_binned_sort = 1;
+    int msm_binned_min_entries = 1 << 16;
     bool ntt_attr_set = false;           // NTT pass kernel's dynamic shared memory opt-in done
     bool msm_attr_set = false;           // accumulate kernel's dynamic shared memory opt-in done
 

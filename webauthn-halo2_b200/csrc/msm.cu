@@ -76,32 +76,36 @@ struct MsmPlan {
 struct RunPlan { uint32_t entries, run, threads, heavy; };  // heavy: buckets queued for msm_combine_heavy_kernel
 
 // ---- recode + histogram -----------------------------------------------------------------------
+// the signed c-bit digits of a canonical scalar, lowest window first: bit 31 = sign, low bits = |d| in [0, 2^(c-1)];
+// the scalar is shifted down by c bits per digit (funnel shifts, no indexed limb access); c <= 31
+struct DigitStream {
+    uint32_t l[8];
+    uint32_t carry;
+    __device__ __forceinline__ explicit DigitStream(const Fr& s) : carry(0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) l[j] = s.l[j];
+    }
+    __device__ __forceinline__ uint32_t next(int c) {
+        uint32_t v = (l[0] & ((1u << c) - 1u)) + carry;
+#pragma unroll
+        for (int j = 0; j < 7; j++) l[j] = __funnelshift_r(l[j], l[j + 1], c);
+        l[7] >>= c;
+        if (v > (1u << (c - 1))) {  // negative digit: v - 2^c
+            carry = 1;
+            return 0x80000000u | ((1u << c) - v);
+        }
+        carry = 0;
+        return v;
+    }
+};
+
 __global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ digits,
                                   uint32_t* __restrict__ counts, size_t n, int c, int windows, int groups, uint32_t nb) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr s = Fr::load_nc(scalars + 2 * i).from_mont();
-    uint32_t carry = 0;
-    const uint32_t half = 1u << (c - 1);
-    const uint32_t mask = (1u << c) - 1u;
+    DigitStream ds(Fr::load_nc(scalars + 2 * i).from_mont());
     for (int w = 0; w < windows; w++) {
-        const int bit = w * c;
-        uint32_t v = 0;
-        if (bit < 256) {
-            const int limb = bit >> 5, off = bit & 31;
-            uint64_t two = s.l[limb];
-            if (limb + 1 < 8) two |= (uint64_t)s.l[limb + 1] << 32;
-            v = (uint32_t)(two >> off) & mask;
-        }
-        v += carry;
-        uint32_t out = 0;
-        if (v > half) {  // negative digit: v - 2^c
-            carry = 1;
-            out = 0x80000000u | ((1u << c) - v);
-        } else {
-            carry = 0;
-            out = v;
-        }
+        const uint32_t out = ds.next(c);
         digits[(size_t)w * n + i] = out;
         const uint32_t mag = out & 0x7fffffffu;
         if (mag) atomicAdd(&counts[(groups > 1 ? (size_t)w * nb : 0) + (mag - 1)], 1u);
@@ -109,7 +113,7 @@ __global__ void msm_recode_kernel(const uint4* __restrict__ scalars, uint32_t* _
 }
 
 // ---- single-CTA exclusive scan of the bucket counts -> bucket offsets; also fixes the run length ------
-// Tiles of 4096 counts (one uint4 per thread, coalesced); per tile a warp-shuffle scan of the thread
+// Tiles of 16384 counts (sixteen consecutive counts per thread); per tile a warp-shuffle scan of the thread
 // totals, a scan of the 32 warp totals, and a running carry.
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
@@ -122,30 +126,49 @@ __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 
 __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
                                                         RunPlan* __restrict__ plan, size_t total, uint32_t max_threads) {
+    constexpr int kPer = 16;   // counts per thread and tile: four 128-bit loads in flight, one block scan per 16384 counts
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) carry = 0;
     __syncthreads();
-    for (size_t base = 0; base < total; base += 4096) {
-        const size_t idx = base + 4 * (size_t)t;
-        uint32_t cnt[4] = {0, 0, 0, 0};
-        if (idx + 3 < total) {
-            const uint4 v = *reinterpret_cast<const uint4*>(counts + idx);
-            cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
+    for (size_t base = 0; base < total; base += 1024 * kPer) {
+        const size_t idx = base + kPer * (size_t)t;
+        uint32_t cnt[kPer];
+        if (idx + kPer <= total) {
+#pragma unroll
+            for (int q = 0; q < kPer / 4; q++) {
+                const uint4 v = *reinterpret_cast<const uint4*>(counts + idx + 4 * q);
+                cnt[4 * q] = v.x; cnt[4 * q + 1] = v.y; cnt[4 * q + 2] = v.z; cnt[4 * q + 3] = v.w;
+            }
         } else {
-            for (int j = 0; j < 4; j++) if (idx + j < total) cnt[j] = counts[idx + j];
+#pragma unroll
+            for (int j = 0; j < kPer; j++) cnt[j] = idx + j < total ? counts[idx + j] : 0u;
         }
-        const uint32_t tot = cnt[0] + cnt[1] + cnt[2] + cnt[3];
+        uint32_t tot = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) tot += cnt[j];
         const uint32_t inc = warp_inclusive_scan(tot, lane);
         if (lane == 31) wsum[warp] = inc;
         __syncthreads();
         if (warp == 0) wsum[lane] = warp_inclusive_scan(wsum[lane], lane);
         __syncthreads();
         uint32_t run = carry + (warp ? wsum[warp - 1] : 0u) + inc - tot;
+        if (idx + kPer <= total) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            if (idx + j < total) { offsets[idx + j] = run; run += cnt[j]; }
+            for (int q = 0; q < kPer / 4; q++) {
+                uint4 o;
+                o.x = run; run += cnt[4 * q];
+                o.y = run; run += cnt[4 * q + 1];
+                o.z = run; run += cnt[4 * q + 2];
+                o.w = run; run += cnt[4 * q + 3];
+                *reinterpret_cast<uint4*>(offsets + idx + 4 * q) = o;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                if (idx + j < total) { offsets[idx + j] = run; run += cnt[j]; }
+            }
         }
         __syncthreads();
         if (t == 0) carry += wsum[31];
@@ -177,6 +200,245 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ digits, const ui
     const uint32_t pos = offsets[b] + atomicAdd(&cursor[b], 1u);
     const uint32_t pidx = table ? (uint32_t)e : (uint32_t)i;  // table[w*n + i] = 2^(c w) P_i
     sorted[pos] = (d & 0x80000000u) | pidx;
+}
+
+// ---- binned counting sort: the same bucket order without one L2 atomic per entry ---------------------------
+// The direct sort above pays two global atomics per entry (histogram, cursor): 2 x 8.4 M at 2^19 points, 230 us, and
+// far worse when a witness column piles its entries on a few buckets.  Here the bucket id is split into a coarse bin
+// (id >> 7) and a fine index (id & 127), and every count / rank is taken in SHARED memory:
+//   bin_count    each CTA recodes a stripe of scalars and histograms the coarse bins in shared memory; one global add
+//                per (CTA, bin).
+//   bin_scan     one CTA: bin offsets (each bin padded to a multiple of four entries so that a chunk is a legal bulk
+//                copy) and the number of 4096-entry chunks per bin.
+//   bin_scatter  recodes again, ranks its entries per bin in shared memory, reserves a range per (CTA, bin) with one
+//                global add and writes the entries, packed as fine | sign | point id, bin by bin.
+//   fine_count   one CTA per chunk: the chunk (16 KB, contiguous) is staged into shared memory by ONE bulk copy (TMA,
+//                cp.async.bulk completing on an mbarrier), histogrammed over the bin's 128 buckets in shared memory, and
+//                the chunk's count per bucket is added to the global bucket count - the value the add returns is the
+//                chunk's base inside the bucket, kept for the last step.
+//   (msm_scan_kernel: bucket offsets and the run plan, as before)
+//   fine_scatter the chunk is staged again, every entry takes its rank from a shared-memory cursor that starts at
+//                offsets[bucket] + the chunk's base, and lands in its final slot.
+// Equal values in a warp (constant stretches of a grand product, zero-heavy limbs) are counted with one shared-memory
+// add per warp (match_all), so skewed columns cost no more than uniform ones.
+constexpr int kFineBits = 7;
+constexpr int kFine = 1 << kFineBits;
+constexpr int kMaxBins = 4096;
+constexpr int kBinThreads = 1024;
+constexpr int kMaxWindows = 32;        // msm_prepare_basis / msm_enqueue keep the binned path to at most 32 windows
+constexpr int kChunk = 4096;            // entries per chunk: 16 KB of shared memory
+constexpr int kChunkThreads = 512;
+constexpr size_t kBinnedMaxEntries = (size_t)1 << 24;   // packed entry: 7 bits fine, 1 bit sign, 24 bits point id
+
+// one more entry for `key` in the shared-memory table: lanes whose keys all agree add once per warp.
+// Must be called by all 32 lanes (inactive lanes pass active = false); returns the entry's rank.
+__device__ __forceinline__ uint32_t smem_rank(uint32_t* table, uint32_t key, bool active, int lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, active);
+    uint32_t r = 0;
+    if (active) {
+        int same = 0;
+#ifndef ZKW_MSM_NO_MATCH
+        __match_all_sync(mask, key, &same);
+#endif
+        if (same) {
+            const int leader = __ffs(mask) - 1;
+            if (lane == leader) r = atomicAdd(&table[key], (uint32_t)__popc(mask));
+            r = __shfl_sync(mask, r, leader) + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+        } else {
+            r = atomicAdd(&table[key], 1u);
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(kBinThreads) msm_bin_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ bin_counts,
+                                                                    size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins) {
+    __shared__ uint32_t s_cnt[kMaxBins];
+    const int lane = threadIdx.x & 31;
+    for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
+    __syncthreads();
+    for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
+        const size_t i = base + threadIdx.x;
+        Fr s = Fr::zero();
+        if (i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
+        DigitStream ds(s);
+        for (int w = 0; w < windows; w++) {
+            const uint32_t mag = ds.next(c) & 0x7fffffffu;
+            const uint32_t id = (groups > 1 ? (uint32_t)w * nb : 0u) + (mag - 1u);
+            smem_rank(s_cnt, id >> kFineBits, mag != 0, lane);
+        }
+    }
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) {
+        const uint32_t v = s_cnt[b];
+        if (v) atomicAdd(&bin_counts[b], v);
+    }
+}
+
+// one CTA, nbins <= 4096: bin_offsets (padded to multiples of four entries) and chunk_first, both exclusive scans with
+// the total in slot [nbins]
+__global__ void __launch_bounds__(1024) msm_bin_scan_kernel(const uint32_t* __restrict__ bin_counts, uint32_t* __restrict__ bin_offsets,
+                                                            uint32_t* __restrict__ chunk_first, uint32_t nbins) {
+    __shared__ uint32_t wsum_p[32], wsum_c[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t pad[4], ch[4];
+    uint32_t tot_p = 0, tot_c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t idx = 4u * (uint32_t)t + (uint32_t)j;
+        const uint32_t cnt = idx < nbins ? bin_counts[idx] : 0u;
+        pad[j] = (cnt + 3u) & ~3u;
+        ch[j] = (cnt + (uint32_t)kChunk - 1u) / (uint32_t)kChunk;
+        tot_p += pad[j];
+        tot_c += ch[j];
+    }
+    const uint32_t inc_p = warp_inclusive_scan(tot_p, lane), inc_c = warp_inclusive_scan(tot_c, lane);
+    if (lane == 31) { wsum_p[warp] = inc_p; wsum_c[warp] = inc_c; }
+    __syncthreads();
+    if (warp == 0) {
+        wsum_p[lane] = warp_inclusive_scan(wsum_p[lane], lane);
+        wsum_c[lane] = warp_inclusive_scan(wsum_c[lane], lane);
+    }
+    __syncthreads();
+    uint32_t run_p = (warp ? wsum_p[warp - 1] : 0u) + inc_p - tot_p;
+    uint32_t run_c = (warp ? wsum_c[warp - 1] : 0u) + inc_c - tot_c;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t idx = 4u * (uint32_t)t + (uint32_t)j;
+        if (idx < nbins) { bin_offsets[idx] = run_p; chunk_first[idx] = run_c; }
+        run_p += pad[j];
+        run_c += ch[j];
+    }
+    if (t == 1023) { bin_offsets[nbins] = run_p; chunk_first[nbins] = run_c; }
+}
+
+__global__ void __launch_bounds__(kBinThreads) msm_bin_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ bin_offsets,
+                                                                      uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ part,
+                                                                      size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins, int table) {
+    __shared__ uint32_t s_cnt[kMaxBins];
+    __shared__ uint32_t s_base[kMaxBins];
+    const int lane = threadIdx.x & 31;
+    for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
+        for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
+        __syncthreads();
+        const size_t i = base + threadIdx.x;
+        Fr s = Fr::zero();
+        if (i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
+        // one counting round: the rank of every entry inside its (stripe, bin) stays in registers, two 16-bit ranks per
+        // word (a stripe has at most 1024 * 32 entries)
+        uint32_t rk[kMaxWindows / 2];
+        {
+            DigitStream ds(s);
+#pragma unroll
+            for (int w = 0; w < kMaxWindows; w++) {
+                if (w < windows) {
+                    const uint32_t mag = ds.next(c) & 0x7fffffffu;
+                    const uint32_t id = (groups > 1 ? (uint32_t)w * nb : 0u) + (mag - 1u);
+                    const uint32_t r = smem_rank(s_cnt, id >> kFineBits, mag != 0, lane);
+                    if (w & 1) rk[w >> 1] |= r << 16; else rk[w >> 1] = r;
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) {
+            const uint32_t v = s_cnt[b];
+            s_base[b] = v ? bin_offsets[b] + atomicAdd(&bin_cursor[b], v) : 0u;
+        }
+        __syncthreads();
+        {
+            DigitStream ds(s);
+#pragma unroll
+            for (int w = 0; w < kMaxWindows; w++) {
+                if (w < windows) {
+                    const uint32_t d = ds.next(c);
+                    const uint32_t mag = d & 0x7fffffffu;
+                    if (mag) {
+                        const uint32_t id = (groups > 1 ? (uint32_t)w * nb : 0u) + (mag - 1u);
+                        const uint32_t r = (rk[w >> 1] >> ((w & 1) * 16)) & 0xffffu;
+                        const uint32_t pidx = table ? (uint32_t)((size_t)w * n + i) : (uint32_t)i;   // table[w*n + i] = 2^(c w) P_i
+                        part[s_base[id >> kFineBits] + r] = ((id & (uint32_t)(kFine - 1)) << 25) | ((d >> 31) << 24) | pidx;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// chunk j -> (bin, first entry, length): bins with no chunk share chunk_first with their successor, so the bin is the
+// LAST one whose chunk_first is <= j
+__device__ __forceinline__ void chunk_range(const uint32_t* __restrict__ bin_offsets, const uint32_t* __restrict__ bin_counts,
+                                            const uint32_t* __restrict__ chunk_first, uint32_t nbins, uint32_t j,
+                                            uint32_t* bin, uint32_t* start, uint32_t* len) {
+    uint32_t lo = 0, hi = nbins;   // chunk_first[lo] <= j < chunk_first[hi]
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (chunk_first[mid] <= j) lo = mid; else hi = mid;
+    }
+    const uint32_t piece = j - chunk_first[lo];
+    const uint32_t left = bin_counts[lo] - piece * (uint32_t)kChunk;
+    *bin = lo;
+    *start = bin_offsets[lo] + piece * (uint32_t)kChunk;
+    *len = left < (uint32_t)kChunk ? left : (uint32_t)kChunk;
+}
+
+__global__ void __launch_bounds__(kChunkThreads) msm_fine_count_kernel(const uint32_t* __restrict__ part, const uint32_t* __restrict__ bin_offsets,
+                                                                       const uint32_t* __restrict__ bin_counts, const uint32_t* __restrict__ chunk_first,
+                                                                       uint32_t nbins, uint32_t* __restrict__ counts, uint32_t* __restrict__ chunk_base) {
+    __shared__ __align__(128) uint32_t s_e[kChunk];
+    __shared__ uint32_t s_cnt[kFine];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t j = blockIdx.x;
+    if (j >= chunk_first[nbins]) return;
+    uint32_t bin, start, len;
+    chunk_range(bin_offsets, bin_counts, chunk_first, nbins, j, &bin, &start, &len);
+    if (threadIdx.x < kFine) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        bulk_load(s_e, part + start, ((len + 3u) & ~3u) * 4u, &bar);   // bins are padded to four entries: a legal bulk copy
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kChunk; k += kChunkThreads) {
+        const bool valid = k < len;
+        const uint32_t e = valid ? s_e[k] : 0u;
+        smem_rank(s_cnt, e >> 25, valid, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x < kFine) {
+        const uint32_t v = s_cnt[threadIdx.x];
+        chunk_base[(size_t)j * kFine + threadIdx.x] = v ? atomicAdd(&counts[(size_t)bin * kFine + threadIdx.x], v) : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kChunkThreads) msm_fine_scatter_kernel(const uint32_t* __restrict__ part, const uint32_t* __restrict__ bin_offsets,
+                                                                         const uint32_t* __restrict__ bin_counts, const uint32_t* __restrict__ chunk_first,
+                                                                         uint32_t nbins, const uint32_t* __restrict__ offsets,
+                                                                         const uint32_t* __restrict__ chunk_base, uint32_t* __restrict__ sorted) {
+    __shared__ __align__(128) uint32_t s_e[kChunk];
+    __shared__ uint32_t s_cur[kFine];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t j = blockIdx.x;
+    if (j >= chunk_first[nbins]) return;
+    uint32_t bin, start, len;
+    chunk_range(bin_offsets, bin_counts, chunk_first, nbins, j, &bin, &start, &len);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        bulk_load(s_e, part + start, ((len + 3u) & ~3u) * 4u, &bar);
+    }
+    if (threadIdx.x < kFine) s_cur[threadIdx.x] = offsets[(size_t)bin * kFine + threadIdx.x] + chunk_base[(size_t)j * kFine + threadIdx.x];
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const int lane = threadIdx.x & 31;
+#pragma unroll 1
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kChunk; k += kChunkThreads) {
+        const bool valid = k < len;
+        const uint32_t e = valid ? s_e[k] : 0u;
+        const uint32_t pos = smem_rank(s_cur, e >> 25, valid, lane);
+        if (valid) sorted[pos] = (((e >> 24) & 1u) << 31) | (e & 0x00ffffffu);
+    }
 }
 
 // ---- accumulate: one thread per run of plan->run consecutive sorted entries ----------------------------
@@ -569,11 +831,19 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     const size_t n_partials = acc_threads + tb;   // slot t + b, t < acc_threads, b < tb
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_digits = take(p.max_entries() * 4);
+    // binned sort (the default wherever its packed entry fits): bucket id = bin * 128 + fine
+    const uint32_t nbins = (uint32_t)(tb >> kFineBits);
+    const bool binned = ctx->msm_binned_sort && (tb & (kFine - 1)) == 0 && nbins >= 1 && nbins <= (uint32_t)kMaxBins &&
+                        p.max_entries() <= kBinnedMaxEntries && p.windows <= kMaxWindows && p.max_entries() >= (size_t)ctx->msm_binned_min_entries;
+    const size_t max_chunks = binned ? (size_t)nbins + p.max_entries() / kChunk + 1 : 0;
+    const size_t o_digits = take((p.max_entries() + (binned ? 4 * (size_t)nbins + 4 : 0)) * 4);   // binned: the partitioned entries, bins padded
     const size_t o_sorted = take(p.max_entries() * 4);
     const size_t o_counts = take(tb * 4);
-    const size_t o_cursor = take(tb * 4);
+    const size_t o_cursor = take(tb * 4);        // binned: bin_counts | bin_cursor (2 * nbins <= tb words)
     const size_t o_offsets = take((tb + 1) * 4);
+    const size_t o_bin_offsets = take(((size_t)nbins + 1) * 4);
+    const size_t o_chunk_first = take(((size_t)nbins + 1) * 4);
+    const size_t o_chunk_base = take(max_chunks * kFine * 4);
     const size_t o_plan = take(sizeof(RunPlan));
     const size_t o_heavy = take(tb * 4);
     const size_t o_partials = take(n_partials * 128);
@@ -605,12 +875,33 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
     // (partial slots that no run writes - a run boundary coinciding with a bucket boundary, empty buckets - are
     // never read either: a bucket's slot range covers exactly the runs that intersect it)
+    if (binned) {
+        uint32_t* bin_counts = cursor;
+        uint32_t* bin_cursor = cursor + nbins;
+        uint32_t* bin_offsets = (uint32_t*)(ws + o_bin_offsets);
+        uint32_t* chunk_first = (uint32_t*)(ws + o_chunk_first);
+        uint32_t* chunk_base = (uint32_t*)(ws + o_chunk_base);
+        const unsigned stripes = (unsigned)std::min<size_t>((n + kBinThreads - 1) / kBinThreads, 2 * (size_t)ctx->sm_count);
+        { ProfScope ps_(ctx, "msm_bin_count_kernel", st); msm_bin_count_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_counts, n, c, p.windows, p.groups, p.nb, nbins); }
+        ZKW_LAUNCHED(ctx);
+        { ProfScope ps_(ctx, "msm_bin_scan_kernel", st); msm_bin_scan_kernel<<<1, 1024, 0, st>>>(bin_counts, bin_offsets, chunk_first, nbins); }
+        ZKW_LAUNCHED(ctx);
+        { ProfScope ps_(ctx, "msm_bin_scatter_kernel", st); msm_bin_scatter_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_offsets, bin_cursor, digits, n, c, p.windows, p.groups, p.nb, nbins, table ? 1 : 0); }
+        ZKW_LAUNCHED(ctx);
+        { ProfScope ps_(ctx, "msm_fine_count_kernel", st); msm_fine_count_kernel<<<(unsigned)max_chunks, kChunkThreads, 0, st>>>(digits, bin_offsets, bin_counts, chunk_first, nbins, counts, chunk_base); }
+        ZKW_LAUNCHED(ctx);
+        { ProfScope ps_(ctx, "msm_scan_kernel", st); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, plan, tb, (uint32_t)acc_threads); }
+        ZKW_LAUNCHED(ctx);
+        { ProfScope ps_(ctx, "msm_fine_scatter_kernel", st); msm_fine_scatter_kernel<<<(unsigned)max_chunks, kChunkThreads, 0, st>>>(digits, bin_offsets, bin_counts, chunk_first, nbins, offsets, chunk_base, sorted); }
+        ZKW_LAUNCHED(ctx);
+    } else {
     { ProfScope ps_(ctx, "msm_recode_kernel", st); msm_recode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const uint4*)scalars_dev, digits, counts, n, c, p.windows, p.groups, p.nb); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_scan_kernel", st); msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, plan, tb, (uint32_t)acc_threads); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_scatter_kernel", st); msm_scatter_kernel<<<(unsigned)((p.max_entries() + 255) / 256), 256, 0, st>>>(digits, offsets, cursor, sorted, n, p.windows, p.groups, p.nb, table ? 1 : 0); }
     ZKW_LAUNCHED(ctx);
+    }
     if (kAccSmemReserve > 0 && !ctx->msm_attr_set) {
         ZKW_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAccSmemReserve));
         ctx->msm_attr_set = true;

@@ -17,6 +17,7 @@
 //
 // The kernel is integer-ALU bound (one 254-bit Montgomery product per butterfly), not HBM bound;
 // see DESIGN.md for the roofline.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -57,6 +58,7 @@ struct NttPassArgs {
     int coset;       // first pass: multiply source element j by zeta^(j mod 3)
     int scale;       // last pass: multiply output element i by scale3[i mod 3]
     int last;        // last pass: outputs leave the lazy range [0, 4r) for [0, r)
+    int zero_stages; // first pass of a zero-padded transform: in stages below this the odd input of every butterfly is zero
     Fr zeta, zeta2;
     Fr scale3[3];
     const uint4* stw;   // staged twiddles of this pass's LAST stage, one contiguous block per tile group, or nullptr
@@ -104,6 +106,13 @@ __device__ __forceinline__ void ntt_round(uint4* slo, uint4* shi, const NttPassA
                 const unsigned el = e & ((1 << u) - 1);
                 // elements live in [0, 4r) between stages (Harvey): one conditional subtraction per butterfly
                 Fr tv;
+                if (s + u < a.zero_stages) {
+                    // zero-padded source (coeff_to_extended: 2^k coefficients in a 2^(k+2) transform): after the bit-reversed
+                    // gather the elements whose low log_n - src_log_n index bits are not all zero are zero, so in the first
+                    // log_n - src_log_n stages every butterfly is (x, 0) -> (x, x): no twiddle, no product
+                    x[e | (1 << u)] = x[e];
+                    continue;
+                }
                 if (s + u == 0) {
                     tv = x[e | (1 << u)].reduced_2m();  // stage 0: every twiddle is 1
                 } else {
@@ -388,6 +397,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         }
     }
     const int npass = (int)plan.size();
+    static const bool zero_skip = !getenv("ZKW_NTT_NO_ZERO_SKIP");   // A/B knob
     // The first pass permutes (bit reversal), so it cannot run in place when there are several
     // tiles: route it through the scratch buffer unless src and dst already differ.
     const bool in_place = (const void*)src_dev == (const void*)dst_dev;
@@ -424,6 +434,7 @@ int ntt_run(zkw_ctx* ctx, const uint64_t* src_dev, unsigned src_log_n, uint64_t*
         a.first = (p == 0);
         a.scale = (p == npass - 1 && scale3) ? 1 : 0;
         a.last = (p == npass - 1) ? 1 : 0;
+        a.zero_stages = (p == 0 && zero_skip) ? std::min<int>((int)(log_n - src_log_n), B) : 0;
         uint64_t* out = dst_dev;
         if (p == 0 && tmp && npass > 1) out = tmp;             // a -> tmp, later passes tmp -> ... -> a
         if (p > 0 && p < npass - 1 && tmp) out = tmp;          // middle passes stay in tmp (tile-local in place)
