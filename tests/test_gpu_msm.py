@@ -128,13 +128,13 @@ def test_msm_skewed_scalars_over_window_tables(zkw, oracle, kind):
         c.close()
 
 
-@pytest.mark.parametrize("binned", [0, 1])
+@pytest.mark.parametrize("sort", ["direct", "binned"])
 @pytest.mark.parametrize("n", [33, 1000, 4097, (1 << 14) + 7])
-def test_msm_both_entry_sorts(zkw, oracle, monkeypatch, binned, n):
+def test_msm_both_entry_sorts(zkw, oracle, monkeypatch, sort, n):
     """The bucket order of the entries comes from one of two sorts (msm.cu): the direct one (a global atomic per entry) and
     the binned one (coarse bins, shared-memory counting, chunks staged by bulk copy).  Both are forced here on every size,
     with uniform and with skewed scalars, over window tables and over caller bases."""
-    monkeypatch.setenv("ZKW_MSM_BINNED_SORT", str(binned))
+    monkeypatch.setenv("ZKW_MSM_BINNED_SORT", "0" if sort == "direct" else "1")
     monkeypatch.setenv("ZKW_MSM_BINNED_MIN_ENTRIES", "0")
     g = _bases(oracle, n, 4000 + n)
     rng = np.random.default_rng(n)

@@ -53,6 +53,12 @@ struct G1Xyzz {
         r.x = Fq::load(c); r.y = Fq::load(c + 32); r.zz = Fq::load(c + 64); r.zzz = Fq::load(c + 96);
         return r;
     }
+    __device__ __forceinline__ static G1Xyzz load_cg(const void* p) {
+        const char* c = reinterpret_cast<const char*>(p);
+        G1Xyzz r;
+        r.x = Fq::load_cg(c); r.y = Fq::load_cg(c + 32); r.zz = Fq::load_cg(c + 64); r.zzz = Fq::load_cg(c + 96);
+        return r;
+    }
     __host__ __device__ __forceinline__ void store(void* p) const {
         char* c = reinterpret_cast<char*>(p);
         x.store(c); y.store(c + 32); zz.store(c + 64); zzz.store(c + 96);

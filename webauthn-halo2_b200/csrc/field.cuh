@@ -218,6 +218,14 @@ struct Fp {
         r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
         return r;
     }
+    __device__ __forceinline__ static Fp load_cg(const void* p) {  // L2 only: data another CTA of the same launch just wrote
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 lo = __ldcg(q), hi = __ldcg(q + 1);
+        Fp r;
+        r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+        r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+        return r;
+    }
     __host__ __device__ __forceinline__ void store(void* p) const {
         uint4* q = reinterpret_cast<uint4*>(p);
         q[0] = make_uint4(l[0], l[1], l[2], l[3]);

@@ -59,7 +59,8 @@ constexpr int kAccThreads = 128;
 #define ZKW_MSM_MIN_RUN 16
 #endif
 constexpr int kMinRun = ZKW_MSM_MIN_RUN;        // shortest run worth a thread (small MSMs use fewer threads instead)
-constexpr int kLight = ZKW_MSM_WAVES > 1 ? 16 : 8;          // partials per bucket folded by one thread; more -> queued for a CTA
+constexpr int kLight = ZKW_MSM_WAVES > 1 ? 16 : 8;          // partials per bucket folded by one thread; more -> queued
+constexpr int kMedium = 128;        // up to this many partials a queued bucket gets one warp, above it a CTA (or several)
 constexpr int kReduceThreads = 64;  // CTA size of the row / column bucket reduction (one warp per row or column)
 
 struct MsmPlan {
@@ -73,7 +74,7 @@ struct MsmPlan {
 };
 
 // device-side run plan, written by the scan kernel once the number of entries is known
-struct RunPlan { uint32_t entries, run, threads, heavy; };  // heavy: buckets queued for msm_combine_heavy_kernel
+struct RunPlan { uint32_t entries, run, threads, heavy, medium; };  // heavy / medium: buckets queued for msm_combine_heavy_kernel / msm_combine_medium_kernel
 
 // ---- recode + histogram -----------------------------------------------------------------------
 // the signed c-bit digits of a canonical scalar, lowest window first: bit 31 = sign, low bits = |d| in [0, 2^(c-1)];
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(1024) msm_scan_kernel(const uint32_t* __restri
         plan->run = run;
         plan->threads = (e + run - 1) / run;
         plan->heavy = 0;
+        plan->medium = 0;
     }
 }
 
@@ -219,8 +221,8 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ digits, const ui
 //   (msm_scan_kernel: bucket offsets and the run plan, as before)
 //   fine_scatter the chunk is staged again, every entry takes its rank from a shared-memory cursor that starts at
 //                offsets[bucket] + the chunk's base, and lands in its final slot.
-// Equal values in a warp (constant stretches of a grand product, zero-heavy limbs) are counted with one shared-memory
-// add per warp (match_all), so skewed columns cost no more than uniform ones.
+// Skewed columns (constant stretches of a grand product, zero-heavy limbs) pile onto few shared-memory words, which the
+// hardware serialises at one lane per clock: they cost less than uniform ones.
 constexpr int kFineBits = 7;
 constexpr int kFine = 1 << kFineBits;
 constexpr int kMaxBins = 4096;
@@ -230,31 +232,17 @@ constexpr int kChunk = 4096;            // entries per chunk: 16 KB of shared me
 constexpr int kChunkThreads = 512;
 constexpr size_t kBinnedMaxEntries = (size_t)1 << 24;   // packed entry: 7 bits fine, 1 bit sign, 24 bits point id
 
-// one more entry for `key` in the shared-memory table: lanes whose keys all agree add once per warp.
-// Must be called by all 32 lanes (inactive lanes pass active = false); returns the entry's rank.
-__device__ __forceinline__ uint32_t smem_rank(uint32_t* table, uint32_t key, bool active, int lane) {
-    const unsigned mask = __ballot_sync(0xffffffffu, active);
-    uint32_t r = 0;
-    if (active) {
-        int same = 0;
-#ifndef ZKW_MSM_NO_MATCH
-        __match_all_sync(mask, key, &same);
-#endif
-        if (same) {
-            const int leader = __ffs(mask) - 1;
-            if (lane == leader) r = atomicAdd(&table[key], (uint32_t)__popc(mask));
-            r = __shfl_sync(mask, r, leader) + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-        } else {
-            r = atomicAdd(&table[key], 1u);
-        }
-    }
-    return r;
+// one more entry for `key` in the shared-memory table; returns the entry's rank.  (Aggregating the lanes of a warp that
+// agree on the key with match_all before the add was measured and dropped: the hardware already serialises same-address
+// shared-memory atomics at one lane per clock, faster than the two per lane of spread addresses - a permuted lookup
+// column's bin_scatter takes 43 us without the aggregation, 47 us with it.)
+__device__ __forceinline__ uint32_t smem_rank(uint32_t* table, uint32_t key, bool active) {
+    return active ? atomicAdd(&table[key], 1u) : 0u;
 }
 
 __global__ void __launch_bounds__(kBinThreads) msm_bin_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ bin_counts,
                                                                     size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins) {
     __shared__ uint32_t s_cnt[kMaxBins];
-    const int lane = threadIdx.x & 31;
     for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
     __syncthreads();
     for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
@@ -265,7 +253,7 @@ __global__ void __launch_bounds__(kBinThreads) msm_bin_count_kernel(const uint4*
         for (int w = 0; w < windows; w++) {
             const uint32_t mag = ds.next(c) & 0x7fffffffu;
             const uint32_t id = (groups > 1 ? (uint32_t)w * nb : 0u) + (mag - 1u);
-            smem_rank(s_cnt, id >> kFineBits, mag != 0, lane);
+            smem_rank(s_cnt, id >> kFineBits, mag != 0);
         }
     }
     __syncthreads();
@@ -317,7 +305,6 @@ __global__ void __launch_bounds__(kBinThreads) msm_bin_scatter_kernel(const uint
                                                                       size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins, int table) {
     __shared__ uint32_t s_cnt[kMaxBins];
     __shared__ uint32_t s_base[kMaxBins];
-    const int lane = threadIdx.x & 31;
     for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
         for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
         __syncthreads();
@@ -334,7 +321,7 @@ __global__ void __launch_bounds__(kBinThreads) msm_bin_scatter_kernel(const uint
                 if (w < windows) {
                     const uint32_t mag = ds.next(c) & 0x7fffffffu;
                     const uint32_t id = (groups > 1 ? (uint32_t)w * nb : 0u) + (mag - 1u);
-                    const uint32_t r = smem_rank(s_cnt, id >> kFineBits, mag != 0, lane);
+                    const uint32_t r = smem_rank(s_cnt, id >> kFineBits, mag != 0);
                     if (w & 1) rk[w >> 1] |= r << 16; else rk[w >> 1] = r;
                 }
             }
@@ -365,6 +352,9 @@ __global__ void __launch_bounds__(kBinThreads) msm_bin_scatter_kernel(const uint
     }
 }
 
+// (Ranks from match.any + warp-private counters instead of returning shared-memory atomics were built and measured:
+// bin_scatter 78 -> 133 us, fine_scatter 48 -> 80 us at 2^19 uniform scalars - MATCH.ANY costs more than the atomic it
+// replaces.  Removed.)
 // chunk j -> (bin, first entry, length): bins with no chunk share chunk_first with their successor, so the bin is the
 // LAST one whose chunk_first is <= j
 __device__ __forceinline__ void chunk_range(const uint32_t* __restrict__ bin_offsets, const uint32_t* __restrict__ bin_counts,
@@ -399,12 +389,11 @@ __global__ void __launch_bounds__(kChunkThreads) msm_fine_count_kernel(const uin
     }
     __syncthreads();
     mbar_wait(&bar, 0);
-    const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (uint32_t k = threadIdx.x; k < (uint32_t)kChunk; k += kChunkThreads) {
         const bool valid = k < len;
         const uint32_t e = valid ? s_e[k] : 0u;
-        smem_rank(s_cnt, e >> 25, valid, lane);
+        smem_rank(s_cnt, e >> 25, valid);
     }
     __syncthreads();
     if (threadIdx.x < kFine) {
@@ -431,12 +420,11 @@ __global__ void __launch_bounds__(kChunkThreads) msm_fine_scatter_kernel(const u
     if (threadIdx.x < kFine) s_cur[threadIdx.x] = offsets[(size_t)bin * kFine + threadIdx.x] + chunk_base[(size_t)j * kFine + threadIdx.x];
     __syncthreads();
     mbar_wait(&bar, 0);
-    const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (uint32_t k = threadIdx.x; k < (uint32_t)kChunk; k += kChunkThreads) {
         const bool valid = k < len;
         const uint32_t e = valid ? s_e[k] : 0u;
-        const uint32_t pos = smem_rank(s_cur, e >> 25, valid, lane);
+        const uint32_t pos = smem_rank(s_cur, e >> 25, valid);
         if (valid) sorted[pos] = (((e >> 24) & 1u) << 31) | (e & 0x00ffffffu);
     }
 }
@@ -516,7 +504,8 @@ __global__ void __launch_bounds__(128) msm_combine_light_kernel(const uint4* __r
     size_t first;
     uint32_t count;
     bucket_partials(offsets, plan->run, b, &first, &count);
-    if (count > (uint32_t)kLight) { heavy_list[atomicAdd(&plan->heavy, 1u)] = b; return; }
+    if (count > (uint32_t)kMedium) { heavy_list[atomicAdd(&plan->heavy, 1u)] = b; return; }
+    if (count > (uint32_t)kLight) { heavy_list[total_buckets - 1u - atomicAdd(&plan->medium, 1u)] = b; return; }   // medium queue grows down from the end of the list
     G1Xyzz acc = G1Xyzz::identity();   // all-zero = identity (ZZ = 0): what an empty bucket stores
     if (count) acc = G1Xyzz::load(partials + 8 * first);
     for (uint32_t i = 1; i < count; i++) {
@@ -526,25 +515,42 @@ __global__ void __launch_bounds__(128) msm_combine_light_kernel(const uint4* __r
     acc.store(buckets + 8 * (size_t)b);
 }
 
-// one CTA per queued bucket (grid-stride over the list), i.e. buckets cut into more than kLight runs (skewed scalars: zeros, bits,
-// tiny digits of sorted lookup columns, long constant stretches of a grand product): strided loop, shuffle
-// tree, then the eight warp sums through shared memory - all sharing one instance of the point addition
-// (runtime-counted loop whose operand comes from memory, from a shuffle, or from shared memory)
+// Queued buckets (cut into more than kLight runs - skewed scalars: zeros, bits, tiny digits of sorted lookup columns, long
+// constant stretches of a grand product), grid-stride over (bucket, segment) items.  A bucket with fewer than 2 * kHeavySeg
+// partials is one item: strided loop, shuffle tree, then the eight warp sums through shared memory - all sharing one instance
+// of the point addition (runtime-counted loop whose operand comes from memory, from a shuffle, or from shared memory).  A
+// heavier bucket (a permuted lookup column leaves three buckets with 8192 partials each) is cut into up to kHeavySplit
+// segments, one CTA each, and the CTA that finishes last (a counter per queued bucket) folds the segment sums: the dependent
+// chain of additions shrinks from count / 256 + 8 to count / 2048 + 8 + 4.
 constexpr int kHeavyThreads = 256;
+constexpr int kHeavySplit = 8;
+constexpr uint32_t kHeavySeg = 512;    // partials per segment below which a bucket is not split further
 __global__ void __launch_bounds__(kHeavyThreads) msm_combine_heavy_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
                                                                           const RunPlan* __restrict__ plan, const uint32_t* __restrict__ heavy_list,
-                                                                          uint4* __restrict__ buckets) {
+                                                                          uint4* __restrict__ buckets, uint4* __restrict__ seg_sums,
+                                                                          uint32_t* __restrict__ seg_done) {
     __shared__ uint4 sh[(kHeavyThreads / 32) * 8];
+    __shared__ uint32_t s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t nheavy = plan->heavy;
+    const uint32_t nitems = plan->heavy * (uint32_t)kHeavySplit;
 #pragma unroll 1
-    for (uint32_t h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const uint32_t h = item / (uint32_t)kHeavySplit, seg = item % (uint32_t)kHeavySplit;
     const uint32_t b = heavy_list[h];
     size_t first;
     uint32_t count;
     bucket_partials(offsets, plan->run, b, &first, &count);
+    uint32_t nseg = count / kHeavySeg;
+    nseg = nseg < 1u ? 1u : (nseg > (uint32_t)kHeavySplit ? (uint32_t)kHeavySplit : nseg);
+    if (seg >= nseg) continue;                                   // CTA-uniform
+    const uint32_t per = (count + nseg - 1) / nseg;
+    const uint32_t lo = seg * per, hi = lo + per < count ? lo + per : count;
+    // phase 0: this segment's partials; phase 1 (last CTA of a split bucket only): the nseg segment sums
+    for (int phase = 0; phase < 2; phase++) {
+    const uint4* src = phase == 0 ? partials + 8 * (first + lo) : seg_sums + 8 * ((size_t)h * kHeavySplit);
+    const uint32_t cnt = phase == 0 ? hi - lo : nseg;
     G1Xyzz acc = G1Xyzz::identity();
-    const int nload = (int)((count + kHeavyThreads - 1) / kHeavyThreads);
+    const int nload = (int)((cnt + kHeavyThreads - 1) / kHeavyThreads);
     const int total_it = nload + 5 + 3;
 #pragma unroll 1
     for (int it = 0; it < total_it; it++) {
@@ -556,7 +562,7 @@ __global__ void __launch_bounds__(kHeavyThreads) msm_combine_heavy_kernel(const 
         G1Xyzz o = G1Xyzz::identity();
         if (it < nload) {
             const uint32_t i = (uint32_t)it * kHeavyThreads + threadIdx.x;
-            if (i < count) o = G1Xyzz::load(partials + 8 * (first + i));
+            if (i < cnt) o = phase == 0 ? G1Xyzz::load(src + 8 * (size_t)i) : G1Xyzz::load_cg(src + 8 * (size_t)i);
         } else if (it < nload + 5) {
             o = shfl_xor_point(acc, 16 >> (it - nload), 0xffffffffu);
         } else {
@@ -564,8 +570,21 @@ __global__ void __launch_bounds__(kHeavyThreads) msm_combine_heavy_kernel(const 
         }
         acc.add(o);
     }
-    if (threadIdx.x == 0) acc.store(buckets + 8 * (size_t)b);
-    __syncthreads();   // sh is reused by the next queued bucket
+    __syncthreads();   // sh is reused by the next phase / item
+    if (nseg == 1 || phase == 1) {
+        if (threadIdx.x == 0) acc.store(buckets + 8 * (size_t)b);
+        break;
+    }
+    // split bucket: publish this segment's sum; whoever arrives last folds them
+    if (threadIdx.x == 0) {
+        acc.store(seg_sums + 8 * ((size_t)h * kHeavySplit + seg));
+        __threadfence();
+        const uint32_t prev = atomicAdd(&seg_done[h], 1u);
+        s_last = prev == nseg - 1 ? 1u : 0u;                       // (seg_done is cleared with the bucket counts, per MSM)
+    }
+    __syncthreads();
+    if (!s_last) break;                                          // CTA-uniform
+    }
     }
 }
 
@@ -606,6 +625,27 @@ __device__ __forceinline__ G1Xyzz warp_strided_sum(const StridedSum& q, int lane
         acc.add(o);
     }
     return acc;  // every lane holds the sum
+}
+
+// buckets with kLight < partials <= kMedium (the real witness column has ~400 of them: the top digits of 88-bit limbs,
+// carries): one warp each - at most four strided loads per lane and the five-level tree - instead of a 256-thread CTA
+// and its eight levels; 4 x SMs CTAs of two warps take the whole queue in one round.
+__global__ void __launch_bounds__(kReduceThreads) msm_combine_medium_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
+                                                                            const RunPlan* __restrict__ plan, const uint32_t* __restrict__ heavy_list,
+                                                                            uint4* __restrict__ buckets, uint32_t total_buckets) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t nwarps = gridDim.x * (kReduceThreads / 32), nmedium = plan->medium;
+#pragma unroll 1
+    for (uint32_t m = blockIdx.x * (kReduceThreads / 32) + (threadIdx.x >> 5); m < nmedium; m += nwarps) {   // warp-uniform
+        const uint32_t b = heavy_list[total_buckets - 1u - m];
+        StridedSum q;
+        q.base = partials;
+        q.stride = 1;
+        q.filter_bit = 32; q.filter_bias = 0;
+        bucket_partials(offsets, plan->run, b, &q.first, &q.count);
+        const G1Xyzz acc = warp_strided_sum(q, lane);
+        if (lane == 0) acc.store(buckets + 8 * (size_t)b);
+    }
 }
 
 __global__ void __launch_bounds__(kReduceThreads) msm_rowcol_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ rc,
@@ -701,8 +741,10 @@ static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
     //   2^20: c=16 3.56, c=17 3.30, c=20 3.76      2^21: c=16 6.82, c=17 6.23, c=20 6.39
     //   2^22: c=17 12.2, c=20 11.6, c=22 14.0      2^24: c=17 48.7, c=20 43.1, c=22 46.1
     //   2^19: c=16 2.02, c=17 2.01 (a tie; 16 keeps the tables' 16 windows)
+    // With the binned entry sort and the cheaper bucket combine (round 2) the 2^19 tie went to c = 17: 15 windows instead of
+    // 16 (-6 % additions) against twice the buckets: MSM 1.709 -> 1.634 ms, k = 19 proof 25.23 -> 24.71 ms (c = 19: 1.865 / 26.12).
     if (n >= (1u << 22)) return 20;
-    if (n >= (1u << 20)) return 17;
+    if (n >= (1u << 19)) return 17;
     return n >= (1u << 13) ? 16 : 8;
 }
 
@@ -840,12 +882,16 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     const size_t o_sorted = take(p.max_entries() * 4);
     const size_t o_counts = take(tb * 4);
     const size_t o_cursor = take(tb * 4);        // binned: bin_counts | bin_cursor (2 * nbins <= tb words)
+    // split heavy buckets: a queued bucket has more than kLight partials, so at most n_partials / kLight of them exist
+    const size_t max_heavy = std::min<size_t>(tb, n_partials / kLight + 1);
+    const size_t o_seg_done = take(max_heavy * 4);   // cleared with counts and cursor
     const size_t o_offsets = take((tb + 1) * 4);
     const size_t o_bin_offsets = take(((size_t)nbins + 1) * 4);
     const size_t o_chunk_first = take(((size_t)nbins + 1) * 4);
     const size_t o_chunk_base = take(max_chunks * kFine * 4);
     const size_t o_plan = take(sizeof(RunPlan));
     const size_t o_heavy = take(tb * 4);
+    const size_t o_seg_sums = take(max_heavy * kHeavySplit * 128);
     const size_t o_partials = take(n_partials * 128);
     const size_t o_buckets = take(tb * 128);
     const int lb = rowcol_lb(c);
@@ -869,10 +915,12 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     RunPlan* plan = (RunPlan*)(ws + o_plan);
     uint32_t* heavy_list = (uint32_t*)(ws + o_heavy);
     uint4* partials = (uint4*)(ws + o_partials);
+    uint4* seg_sums = (uint4*)(ws + o_seg_sums);
+    uint32_t* seg_done = (uint32_t*)(ws + o_seg_done);
     uint4* buckets = (uint4*)(ws + o_buckets);
     uint4* blocks = (uint4*)(ws + o_blocks);
     uint4* outs = (uint4*)(ws + o_out);
-    ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_cursor - o_counts) + tb * 4, st));
+    ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (o_seg_done - o_counts) + max_heavy * 4, st));
     // (partial slots that no run writes - a run boundary coinciding with a bucket boundary, empty buckets - are
     // never read either: a bucket's slot range covers exactly the runs that intersect it)
     if (binned) {
@@ -910,7 +958,9 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_combine_light_kernel", st); msm_combine_light_kernel<<<(unsigned)((tb + 127) / 128), 128, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_combine_heavy_kernel", st); msm_combine_heavy_kernel<<<(unsigned)std::min<size_t>(tb, 2 * (size_t)ctx->sm_count), kHeavyThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets); }
+    { ProfScope ps_(ctx, "msm_combine_heavy_kernel", st); msm_combine_heavy_kernel<<<(unsigned)std::min<size_t>(tb, 2 * (size_t)ctx->sm_count), kHeavyThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets, seg_sums, seg_done); }
+    ZKW_LAUNCHED(ctx);
+    { ProfScope ps_(ctx, "msm_combine_medium_kernel", st); msm_combine_medium_kernel<<<(unsigned)std::min<size_t>((tb + 1) / 2, 4 * (size_t)ctx->sm_count), kReduceThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<<<dim3((rc_per_group + kReduceThreads / 32 - 1) / (kReduceThreads / 32), p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, lb); }
     ZKW_LAUNCHED(ctx);
