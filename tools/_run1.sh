@@ -1,2 +1,6 @@
-for c in 16 17 19 20; do ZKW_MSM_WINDOW_BITS=$c timeout 300 python tools/msm_ab.py 2>&1 | tail -1 | sed "s/^/c=$c /"; done > gpurun_out/s7_window.txt
-cat gpurun_out/s7_window.txt
+ZKW_E2E_TRACE=1 python tools/timeline_e2e.py gpurun_out/s14_timeline_e2e.csv 2>&1 | grep "e2e\|launches" | tail -5 > gpurun_out/s14.txt
+python tools/e2e_parts.py >> gpurun_out/s14.txt 2>&1
+ZKW_SYNTH_NO_WRITEBACK=1 python tools/e2e_parts.py >> gpurun_out/s14.txt 2>&1
+python tools/e2e_parts.py 17 >> gpurun_out/s14.txt 2>&1
+ZKW_SYNTH_NO_WRITEBACK=1 python tools/e2e_parts.py 17 >> gpurun_out/s14.txt 2>&1
+cat gpurun_out/s14.txt

@@ -309,6 +309,8 @@ int zkw_ctx_create(int device, zkw_ctx** out) {
     if (env) ctx->msm_precompute = atoi(env);
     env = getenv("ZKW_MSM_BINNED_SORT");
     if (env) ctx->msm_binned_sort = atoi(env);
+    env = getenv("ZKW_MSM_ZERO_COPY_OUT");
+    if (env) ctx->msm_zero_copy_out = atoi(env);
     env = getenv("ZKW_MSM_BINNED_MIN_ENTRIES");
     if (env) ctx->msm_binned_min_entries = atoi(env);
     *out = ctx;

@@ -63,6 +63,7 @@ struct zkw_ctx {
     // fewer entries than msm_binned_min_entries keep the direct three-kernel sort (fewer launches)
     int msm_binned_sort = 1;
     int msm_binned_min_entries = 1 << 16;
+    int msm_zero_copy_out = 1;           // MSM results written by the kernel into page-locked host memory (ZKW_MSM_ZERO_COPY_OUT=0: D2H copy)
     bool ntt_attr_set = false;           // NTT pass kernel's dynamic shared memory opt-in done
     bool msm_attr_set = false;           // accumulate kernel's dynamic shared memory opt-in done
 

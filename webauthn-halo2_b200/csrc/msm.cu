@@ -964,17 +964,22 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<<<dim3((rc_per_group + kReduceThreads / 32 - 1) / (kReduceThreads / 32), p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, lb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_weighted_kernel", st); msm_weighted_kernel<<<dim3(c, p.groups), 32, 0, st>>>(blocks, outs, p.nb, lb, c); }
-    ZKW_LAUNCHED(ctx);
     const size_t out_bytes = (size_t)p.groups * c * 128;
     if (ctx->lane_pinned_bytes[lane] < out_bytes) {
-        if (ctx->lane_pinned[lane]) cudaFreeHost(ctx->lane_pinned[lane]);
+        if (ctx->lane_pinned[lane]) { cudaStreamSynchronize(st); cudaFreeHost(ctx->lane_pinned[lane]); }
         ctx->lane_pinned[lane] = nullptr;
         ctx->lane_pinned_bytes[lane] = 0;
         ZKW_CUDA(ctx, cudaMallocHost(&ctx->lane_pinned[lane], out_bytes));
         ctx->lane_pinned_bytes[lane] = out_bytes;
     }
-    ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->lane_pinned[lane], outs, out_bytes, cudaMemcpyDeviceToHost, st));
+    // The weighted sums (c x 128 B per group) are stored straight into the lane's page-locked host slot (unified addressing:
+    // the kernel writes over PCIe), not copied back: a D2H copy queued behind this lane's kernels sat in the copy queue and
+    // held back the H2D copy of the advice columns that the end-to-end path issues while this MSM is still running
+    // (measured: the advice arrived 1.1 ms after the random-polynomial MSM had finished instead of under it).
+    uint4* outs_host = ctx->msm_zero_copy_out ? (uint4*)ctx->lane_pinned[lane] : outs;
+    { ProfScope ps_(ctx, "msm_weighted_kernel", st); msm_weighted_kernel<<<dim3(c, p.groups), 32, 0, st>>>(blocks, outs_host, p.nb, lb, c); }
+    ZKW_LAUNCHED(ctx);
+    if (!ctx->msm_zero_copy_out) ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->lane_pinned[lane], outs, out_bytes, cudaMemcpyDeviceToHost, st));
     ctx->lane_groups[lane] = p.groups;
     ctx->lane_c[lane] = c;
     return ZKW_OK;

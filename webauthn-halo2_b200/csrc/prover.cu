@@ -750,8 +750,19 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     // goes first; when the advice is already here it is submitted after the (light) advice and permuted-lookup commitments,
     // which the transcript needs first.
     const bool random_first = ready != nullptr;
+    // ZKW_E2E_TRACE=1 (development aid): host clock at the hand-over points of the overlapped path, on stderr
+    static const bool e2e_trace = getenv("ZKW_E2E_TRACE") != nullptr;
+    timespec tr0;
+    auto trace = [&](const char* what) {
+        if (!e2e_trace) return;
+        timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+        fprintf(stderr, "  [e2e] %-28s %.3f ms\n", what, 1e3 * (double)(t.tv_sec - tr0.tv_sec) + 1e-6 * (double)(t.tv_nsec - tr0.tv_nsec));
+    };
+    if (e2e_trace) clock_gettime(CLOCK_MONOTONIC, &tr0);
     if (random_first) ZKW_TRY(pipe.submit(ZKW_BASES_G, random_poly, &t_random));
+    trace("random MSM submitted");
     if (ready) ZKW_TRY(ready(ready_user));
+    trace("advice ready");
 
     // ---- 1. advice ----
     std::vector<uint64_t*> adv(NA);
@@ -783,6 +794,8 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     // compression is the identity, so A' and S' are functions of the witness alone) and the random polynomial of
     // the vanishing argument.  The transcript still absorbs them in upstream's order (pipe.write below).
     std::vector<int> t_adv(NA), t_lk;
+    trace("advice copies enqueued");
+    if (e2e_trace) { cudaStreamSynchronize(st); trace("advice on the device"); }
     for (unsigned c = 0; c < NA; c++) ZKW_TRY(pipe.submit(ZKW_BASES_G_LAGRANGE, adv[c], &t_adv[c]));
 
     // ---- 2. lookups: permuted input / table ----
