@@ -97,7 +97,7 @@ def test_msm_resident_srs_with_window_tables(zkw, oracle, n):
         c.close()
 
 
-@pytest.mark.parametrize("kind", ["all_equal", "plus_minus_one", "sorted_small", "half_zero", "two_values", "run_aligned"])
+@pytest.mark.parametrize("kind", ["all_equal", "plus_minus_one", "sorted_small", "half_zero", "two_values", "run_aligned", "few_hundred_values"])
 def test_msm_skewed_scalars_over_window_tables(zkw, oracle, kind):
     """Witness-shaped scalar vectors put most entries into a handful of buckets: the equal-run accumulation
     cuts those buckets into thousands of partials (slots t + b) that the queued heavy-bucket kernel folds."""
@@ -114,6 +114,11 @@ def test_msm_skewed_scalars_over_window_tables(zkw, oracle, kind):
         vals = [0 if i % 2 else int(x) for i, x in enumerate(rng.integers(0, 1 << 62, n))]
     elif kind == "two_values":
         vals = [(1 << 200) + 5 if i < n // 3 else (1 << 16) - 1 for i in range(n)]   # digit 2^16 - 1 recodes to -1 with a carry
+    elif kind == "few_hundred_values":
+        # ~160 entries per bucket in window 0 and ~5000 in window 1: 10 and 300 partials - the warp-per-bucket ("medium") and
+        # CTA-per-bucket queues of the combine step, like the top digits of the real witness's 88-bit limbs
+        pool = [int(x) for x in rng.integers(1, 1 << 16, 200)]
+        vals = [pool[int(j)] + (int(j) % 7 << 16) for j in rng.integers(0, 200, n)]
     else:
         vals = [(i // 16) + 1 for i in range(n)]                             # runs of 16 equal digits: run and bucket boundaries coincide
     s = oracle.fr_to_mont(vals)

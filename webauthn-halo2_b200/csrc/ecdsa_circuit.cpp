@@ -28,6 +28,7 @@
 #include <chrono>
 #include <cstdio>
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <thread>
 #include <unordered_map>
@@ -1559,25 +1560,37 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
         uint64_t total = 0;
         for (unsigned i = 0; i < b.A; i++) total += c->st.rows[i];
         const uint64_t work = total - cps[1].cells_before;
-        std::vector<unsigned> cut(nthreads + 1, nseg);
+        // the window segments are cut into chunks of equal cell counts, four per thread, handed out by an atomic counter:
+        // the threads do not run at the same speed (hyper-thread siblings, a busy host), and a static split waited for the
+        // slowest (per-thread CPU times 0.41-0.81 ms for equal cell counts on the GPU box)
+        const unsigned nchunks = std::max(1u, std::min(nseg - 1, 4 * nthreads));
+        std::vector<unsigned> cut(nchunks + 1, nseg);
         cut[0] = 1;
-        for (unsigned t = 1, sgm = 1; t < nthreads; t++) {
-            const uint64_t target = cps[1].cells_before + work * t / nthreads;
+        for (unsigned t = 1, sgm = 1; t < nchunks; t++) {
+            const uint64_t target = cps[1].cells_before + work * t / nchunks;
             while (sgm < nseg && cps[sgm].cells_before < target) sgm++;
             cut[t] = sgm;
         }
         std::vector<Builder> workers(nthreads, b);        // copies: own cursor, shared output columns and pre-pass results
         std::vector<char> done_ok(nthreads, 0);
+        std::atomic<unsigned> next_chunk{0};
         auto body = [&](unsigned t) {
             Builder& w = workers[t];
-            const unsigned s0 = cut[t], s1 = cut[t + 1];
-            if (s0 >= s1) return;
+            timespec ts0, ts1;
+            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts0);
+            unsigned taken = 0;
+            for (;;) {
+            const unsigned ci = next_chunk.fetch_add(1);
+            if (ci >= nchunks) break;
+            const unsigned s0 = cut[ci], s1 = cut[ci + 1];
+            if (s0 >= s1) continue;
+            taken++;
             const auto& cp = cps[s0];
             w.rows = cp.rows;
             w.lk_cursor = cp.lookups_before;
             w.dinv_next = Builder::first_op_of(s0, nw);
             Builder::EPt a2 = acc, f2 = facc;
-            if (t > 0) {
+            if (s0 > 1) {
                 // accumulators at the start of segment s0: variable part after window min(s0, nw) - 1, fixed part after
                 // window s0 - nw - 1 (or its constant start point)
                 const unsigned va = (s0 < nw ? s0 : nw) - 1;
@@ -1589,25 +1602,24 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
                 }
             }
             bool okt = true;
-            timespec ts0, ts1;
-            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts0);
             w.run_segments(rc, s0, s1, a2, f2, &okt);
-            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts1);
-            // hand the rows this thread wrote (thread 0: the prologue's too) to memory before the DMA reads them
+            // hand the rows this chunk wrote (the first chunk: the prologue's too) to memory before the DMA reads them
             for (unsigned i = 0; i < w.A; i++) {
-                const uint64_t r0 = t == 0 ? 0 : cp.rows[i], r1 = w.rows[i];
+                const uint64_t r0 = s0 == 1 ? 0 : cp.rows[i], r1 = w.rows[i];
                 if (r1 > r0) writeback_lines(w.adv[i] + 4 * r0, (size_t)(r1 - r0) * 32);
             }
             if (w.L && !w.selector_mode) {
-                const uint64_t c0 = t == 0 ? 0 : cp.lookups_before, c1 = w.lk_cursor;
+                const uint64_t c0 = s0 == 1 ? 0 : cp.lookups_before, c1 = w.lk_cursor;
                 if (c1 > c0)
                     for (unsigned j = 0; j < w.L; j++) {
                         const uint64_t r0 = c0 / w.L, r1 = std::min<uint64_t>((c1 - 1) / w.L + 1, w.u);
                         if (r1 > r0) writeback_lines(w.adv[w.A + j] + 4 * r0, (size_t)(r1 - r0) * 32);
                     }
             }
-            if (timing) fprintf(stderr, "    thread %u segments [%u,%u) cells %llu cpu %.3f ms\n", t, s0, s1, (unsigned long long)((s1 < nseg ? cps[s1].cells_before : total) - cp.cells_before), (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
             if (s1 == nseg) done_ok[t] = okt ? 1 : 2;
+            }
+            clock_gettime(CLOCK_THREAD_CPUTIME_ID, &ts1);
+            if (timing) fprintf(stderr, "    thread %u: %u chunks, cpu %.3f ms\n", t, taken, (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
         };
         std::vector<std::thread> threads;
         for (unsigned t = 1; t < nthreads; t++) threads.emplace_back(body, t);
