@@ -600,6 +600,7 @@ def run_b200(args):
     # the dominant kernel in isolation (no lanes in flight): one uniform-scalar MSM of 2^k points, the case
     # DESIGN.md's roofline arithmetic is written for
     isolated = None
+    msm_windows = -(-255 // ctx.msm_window_bits(1 << args.k))      # mixed additions per point and MSM (the plan the library picks)
     if args.workload != "hotpath":
         g = torch.Generator(device=torch.device("cuda", local))
         g.manual_seed(99)
@@ -693,7 +694,8 @@ def run_b200(args):
                      "`isolated` times the same kernel alone on uniform scalars"),
             "isolated": isolated,
             "isolated_achieved_gbs": (alg_bytes / (isolated["avg_launch_ms"] / 1000.0) / 1e9) if isolated else None,
-            "isolated_modmul_per_s": (16 * n * 10 / (isolated["avg_launch_ms"] / 1000.0)) if isolated else None,
+            "msm_windows": msm_windows,
+            "isolated_modmul_per_s": (msm_windows * n * 10 / (isolated["avg_launch_ms"] / 1000.0)) if isolated else None,
             "modmul_peak_per_s_measured": modmul_peak, "modmul_peak_source": modmul_src,
         }
         kernels = {name: {"ms_per_step": v[0], "launches_per_step": v[1]} for name, v in sorted(prof_all.items())}

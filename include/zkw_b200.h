@@ -99,6 +99,9 @@ int zkw_srs_load_dev(zkw_ctx* ctx, const uint64_t* g_dev, const uint64_t* g_lagr
  * 2^(c*w)*P_i for every window of the resident bases (c.f. msm.cu). Environment overrides at ctx
  * creation: ZKW_MSM_WINDOW_BITS, ZKW_MSM_PRECOMPUTE. */
 int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute);
+/* Window width c an n-point MSM uses with the current configuration (the MSM makes ceil(255 / c) mixed additions per
+ * point); negative = error.  Reporting aid: bench.py derives its product counts from it. */
+int zkw_msm_window_bits(zkw_ctx* ctx, size_t n);
 
 enum { ZKW_BASES_G = 0, ZKW_BASES_G_LAGRANGE = 1, ZKW_BASES_CALLER = 2 };
 

@@ -361,6 +361,11 @@ void* zkw_ctx_stream(zkw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; 
 const char* zkw_last_cuda_error(zkw_ctx* ctx) { return ctx ? ctx->last_err.c_str() : ""; }
 uint64_t zkw_ctx_launch_count(zkw_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int zkw_msm_window_bits(zkw_ctx* ctx, size_t n) {
+    if (!ctx) return ZKW_ERR_INVALID;
+    return zkw::msm_window_bits(ctx, n);
+}
+
 int zkw_msm_config(zkw_ctx* ctx, int window_bits, int precompute) {
     if (!ctx || window_bits < 0 || window_bits > 24 || window_bits == 1) return ZKW_ERR_INVALID;
     ctx->msm_window_bits = window_bits;

@@ -163,6 +163,7 @@ int msm_lanes_collect(zkw_ctx* ctx, const int* lanes, int count, uint64_t (*outs
 // wait for ONE lane's MSM (host blocks on that lane's event only) and fetch its result
 int msm_lane_wait(zkw_ctx* ctx, int lane, uint64_t out_xyz[12]);
 int msm_prepare_basis(zkw_ctx* ctx, MsmBasis& b);
+int msm_window_bits(const zkw_ctx* ctx, size_t n);   // the window width an n-point MSM uses
 void msm_free_basis(MsmBasis& b);
 int g1_batch_normalize_dev(zkw_ctx* ctx, const uint64_t* xyz_dev, size_t m, uint64_t* out_xy_dev);
 // srs.cu

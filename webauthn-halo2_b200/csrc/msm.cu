@@ -748,6 +748,8 @@ static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
     return n >= (1u << 13) ? 16 : 8;
 }
 
+int msm_window_bits(const zkw_ctx* ctx, size_t n) { return pick_window_bits(ctx, n); }
+
 static void make_plan(MsmPlan& p, size_t n, int c, bool table) {
     p.c = c;
     p.windows = (255 + c - 1) / c;

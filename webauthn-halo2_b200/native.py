@@ -38,7 +38,7 @@ u64p = C.POINTER(C.c_uint64)
 # every symbol include/zkw_b200.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
     "zkw_ctx_create", "zkw_ctx_destroy", "zkw_ctx_sync", "zkw_ctx_stream", "zkw_strerror", "zkw_last_cuda_error",
-    "zkw_ctx_launch_count", "zkw_srs_load", "zkw_srs_load_dev", "zkw_msm_config", "zkw_msm_bn254_g1",
+    "zkw_ctx_launch_count", "zkw_srs_load", "zkw_srs_load_dev", "zkw_msm_config", "zkw_msm_window_bits", "zkw_msm_bn254_g1",
     "zkw_msm_bn254_g1_dev", "zkw_msm_bn254_g1_dev_to_host", "zkw_g1_batch_normalize", "zkw_ntt_bn254_fr",
     "zkw_ntt_bn254_fr_dev", "zkw_lagrange_to_coeff", "zkw_lagrange_to_coeff_dev", "zkw_coeff_to_lagrange",
     "zkw_coeff_to_lagrange_dev", "zkw_coeff_to_extended", "zkw_coeff_to_extended_dev", "zkw_extended_to_coeff",
@@ -284,6 +284,13 @@ class Context:
         self._check(self.lib.zkw_host_alloc(self.h, C.c_size_t(8 * max(count, 1)), C.byref(p)), "zkw_host_alloc")
         self._host_allocs.append(p)
         return np.ctypeslib.as_array(C.cast(p, u64p), shape=(max(count, 1),))[:count]
+
+    def msm_window_bits(self, n: int) -> int:
+        """window width c of an n-point MSM; the MSM makes ceil(255 / c) mixed additions per point"""
+        c = self.lib.zkw_msm_window_bits(self.h, C.c_size_t(n))
+        if c <= 0:
+            raise ZkwError(c, "zkw_msm_window_bits")
+        return int(c)
 
     def msm_config(self, window_bits: int = 0, precompute: bool = True):
         self._check(self.lib.zkw_msm_config(self.h, window_bits, int(precompute)), "zkw_msm_config")
