@@ -495,8 +495,10 @@ __device__ __forceinline__ bool bucket_partials(const uint32_t* __restrict__ off
     return true;
 }
 
-// one thread per bucket: folds up to kLight partials (the common case); heavier buckets are queued for the CTA kernel
-__global__ void __launch_bounds__(128) msm_combine_light_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
+// one thread per bucket: folds up to kLight partials (the common case); heavier buckets are queued for the CTA kernel.
+// (64-thread CTAs, so that the 2^16 buckets of a k = 19 MSM are one resident wave at 140 registers, measured: no change, 47 us.)
+constexpr int kLightThreads = 128;
+__global__ void __launch_bounds__(kLightThreads) msm_combine_light_kernel(const uint4* __restrict__ partials, const uint32_t* __restrict__ offsets,
                                                                 RunPlan* __restrict__ plan, uint32_t* __restrict__ heavy_list,
                                                                 uint4* __restrict__ buckets, uint32_t total_buckets) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -648,35 +650,74 @@ __global__ void __launch_bounds__(kReduceThreads) msm_combine_medium_kernel(cons
     }
 }
 
-__global__ void __launch_bounds__(kReduceThreads) msm_rowcol_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ rc,
-                                                                    uint32_t nb, int lb) {
+// The same sum by a whole CTA of THREADS: strided loads, the five-level shuffle tree, the warp sums through shared memory and
+// log2(THREADS / 32) more shuffle levels in warp 0 - count / THREADS + 5 + log2(THREADS / 32) dependent additions instead of
+// count / 32 + 5 (256 elements, 128 threads: 9 instead of 13), still ONE instance of the addition.  Thread 0 returns the sum.
+template <int THREADS>
+__device__ __forceinline__ G1Xyzz cta_strided_sum(const StridedSum& q, uint4* sh /* (THREADS / 32) * 8 uint4 */) {
+    constexpr int kW = THREADS / 32;
+    constexpr int kLw = kW == 1 ? 0 : (kW == 2 ? 1 : (kW == 4 ? 2 : 3));
+    static_assert(kW == 1 || kW == 2 || kW == 4 || kW == 8, "cta_strided_sum: 32, 64, 128 or 256 threads");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    G1Xyzz acc = G1Xyzz::identity();
+    const int nload = (int)((q.count + THREADS - 1) / THREADS);
+#pragma unroll 1
+    for (int it = 0; it < nload + 5 + kLw; it++) {
+        if (kW > 1 && it == nload + 5) {   // every lane of a warp holds the warp's sum: hand the sums to warp 0
+            if (lane == 0) acc.store(sh + 8 * warp);
+            __syncthreads();
+            acc = (warp == 0 && lane < kW) ? G1Xyzz::load(sh + 8 * lane) : G1Xyzz::identity();
+        }
+        G1Xyzz o = G1Xyzz::identity();
+        if (it < nload) {
+            const uint32_t e = (uint32_t)it * THREADS + threadIdx.x;
+            const bool take = e < q.count && (q.filter_bit >= 32 || (((e + q.filter_bias) >> q.filter_bit) & 1u));
+            if (take) o = G1Xyzz::load(q.base + 8 * (q.first + (size_t)e * q.stride));
+        } else if (it < nload + 5) {
+            o = shfl_xor_point(acc, 16 >> (it - nload), 0xffffffffu);
+        } else {
+            o = shfl_xor_point(acc, (kW / 2) >> (it - nload - 5), 0xffffffffu);
+        }
+        acc.add(o);
+    }
+    return acc;
+}
+
+// THREADS per row / column / weight bit.  These kernels end every MSM and with it every transcript round, at 2-4 % occupancy;
+// what they cost is the dependent chain of additions, until there are enough warps to make them throughput-bound (see the
+// launch site).
+constexpr int kRowThreads = 128;
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) msm_rowcol_kernel(const uint4* __restrict__ buckets, uint4* __restrict__ rc,
+                                                                                     uint32_t nb, int lb) {
+    __shared__ uint4 sh[(THREADS / 32) * 8];
     const uint32_t ncols = 1u << lb, nrows = nb >> lb;
     const uint32_t g = blockIdx.y;
-    const uint32_t id = blockIdx.x * (kReduceThreads / 32) + (threadIdx.x >> 5);   // warp-uniform
-    const int lane = threadIdx.x & 31;
-    if (id >= nrows + ncols) return;
+    const uint32_t id = blockIdx.x;
     StridedSum q;
     q.base = buckets + 8 * (size_t)g * nb;
     q.filter_bit = 32; q.filter_bias = 0;
     if (id < nrows) { q.first = (size_t)id << lb; q.stride = 1; q.count = ncols; }
     else { q.first = id - nrows; q.stride = ncols; q.count = nrows; }
-    const G1Xyzz acc = warp_strided_sum(q, lane);
-    if (lane == 0) acc.store(rc + 8 * ((size_t)g * (nrows + ncols) + id));
+    const G1Xyzz acc = cta_strided_sum<THREADS>(q, sh);
+    if (threadIdx.x == 0) acc.store(rc + 8 * ((size_t)g * (nrows + ncols) + id));
 }
 
 // out[g][j]: j < rbits -> sum of rows whose index has bit j; else sum of columns whose (index + 1) has bit j - rbits
-__global__ void __launch_bounds__(32) msm_weighted_kernel(const uint4* __restrict__ rc, uint4* __restrict__ out,
-                                                          uint32_t nb, int lb, int c) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? 4 : 1) msm_weighted_kernel(const uint4* __restrict__ rc, uint4* __restrict__ out,
+                                                                                       uint32_t nb, int lb, int c) {
+    __shared__ uint4 sh[(THREADS / 32) * 8];
     const uint32_t ncols = 1u << lb, nrows = nb >> lb;
     const int rbits = c - 1 - lb;
-    const int j = blockIdx.x, g = blockIdx.y, lane = threadIdx.x;
+    const int j = blockIdx.x, g = blockIdx.y;
     StridedSum q;
     q.base = rc + 8 * (size_t)g * (nrows + ncols);
     q.stride = 1;
     if (j < rbits) { q.first = 0; q.count = nrows; q.filter_bit = (uint32_t)j; q.filter_bias = 0; }
     else { q.first = nrows; q.count = ncols; q.filter_bit = (uint32_t)(j - rbits); q.filter_bias = 1; }
-    const G1Xyzz acc = warp_strided_sum(q, lane);
-    if (lane == 0) acc.store(out + 8 * ((size_t)g * c + j));
+    const G1Xyzz acc = cta_strided_sum<THREADS>(q, sh);
+    if (threadIdx.x == 0) acc.store(out + 8 * ((size_t)g * c + j));
 }
 
 // ---- window tables for a resident basis: table[w*n + i] = 2^(c w) P_i ----------------------------------
@@ -958,13 +999,17 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     }
     { ProfScope ps_(ctx, "msm_accumulate_kernel", st); msm_accumulate_kernel<<<(unsigned)((acc_threads + kAccThreads - 1) / kAccThreads), kAccThreads, kAccSmemReserve, st>>>((const uint4*)points, sorted, offsets, plan, partials, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_combine_light_kernel", st); msm_combine_light_kernel<<<(unsigned)((tb + 127) / 128), 128, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
+    { ProfScope ps_(ctx, "msm_combine_light_kernel", st); msm_combine_light_kernel<<<(unsigned)((tb + kLightThreads - 1) / kLightThreads), kLightThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_combine_heavy_kernel", st); msm_combine_heavy_kernel<<<(unsigned)std::min<size_t>(tb, 2 * (size_t)ctx->sm_count), kHeavyThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets, seg_sums, seg_done); }
     ZKW_LAUNCHED(ctx);
     { ProfScope ps_(ctx, "msm_combine_medium_kernel", st); msm_combine_medium_kernel<<<(unsigned)std::min<size_t>((tb + 1) / 2, 4 * (size_t)ctx->sm_count), kReduceThreads, 0, st>>>(partials, offsets, plan, heavy_list, buckets, (uint32_t)tb); }
     ZKW_LAUNCHED(ctx);
-    { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<<<dim3((rc_per_group + kReduceThreads / 32 - 1) / (kReduceThreads / 32), p.groups), kReduceThreads, 0, st>>>(buckets, blocks, p.nb, lb); }
+    // Row / column sums: one WARP per sum.  (A CTA of 128 per sum - 9 dependent additions instead of 13 - was measured: 2048
+    // warps instead of 512 turn the kernel from latency-bound into throughput-bound, 88 -> 136 us.)  The 17 weighted sums do
+    // get a CTA each when there is one bucket set: 81 -> 66 us.
+    const bool wide_rows = p.groups == 1;
+    { ProfScope ps_(ctx, "msm_rowcol_kernel", st); msm_rowcol_kernel<32><<<dim3(rc_per_group, p.groups), 32, 0, st>>>(buckets, blocks, p.nb, lb); }
     ZKW_LAUNCHED(ctx);
     const size_t out_bytes = (size_t)p.groups * c * 128;
     if (ctx->lane_pinned_bytes[lane] < out_bytes) {
@@ -979,7 +1024,11 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
     // held back the H2D copy of the advice columns that the end-to-end path issues while this MSM is still running
     // (measured: the advice arrived 1.1 ms after the random-polynomial MSM had finished instead of under it).
     uint4* outs_host = ctx->msm_zero_copy_out ? (uint4*)ctx->lane_pinned[lane] : outs;
-    { ProfScope ps_(ctx, "msm_weighted_kernel", st); msm_weighted_kernel<<<dim3(c, p.groups), 32, 0, st>>>(blocks, outs_host, p.nb, lb, c); }
+    {
+        ProfScope ps_(ctx, "msm_weighted_kernel", st);
+        if (wide_rows) msm_weighted_kernel<kRowThreads><<<dim3(c, p.groups), kRowThreads, 0, st>>>(blocks, outs_host, p.nb, lb, c);
+        else msm_weighted_kernel<32><<<dim3(c, p.groups), 32, 0, st>>>(blocks, outs_host, p.nb, lb, c);
+    }
     ZKW_LAUNCHED(ctx);
     if (!ctx->msm_zero_copy_out) ZKW_CUDA(ctx, cudaMemcpyAsync(ctx->lane_pinned[lane], outs, out_bytes, cudaMemcpyDeviceToHost, st));
     ctx->lane_groups[lane] = p.groups;

@@ -752,7 +752,7 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
     const bool random_first = ready != nullptr;
     // ZKW_E2E_TRACE=1 (development aid): host clock at the hand-over points of the overlapped path, on stderr
     static const bool e2e_trace = getenv("ZKW_E2E_TRACE") != nullptr;
-    timespec tr0;
+    timespec tr0{};
     auto trace = [&](const char* what) {
         if (!e2e_trace) return;
         timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
