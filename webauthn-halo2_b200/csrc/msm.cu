@@ -241,14 +241,15 @@ __device__ __forceinline__ uint32_t smem_rank(uint32_t* table, uint32_t key, boo
 }
 
 __global__ void __launch_bounds__(kBinThreads) msm_bin_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ bin_counts,
-                                                                    size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins) {
+                                                                    size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins,
+                                                                    uint32_t stripe) {
     __shared__ uint32_t s_cnt[kMaxBins];
     for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
     __syncthreads();
-    for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
+    for (size_t base = (size_t)blockIdx.x * stripe; base < n; base += (size_t)gridDim.x * stripe) {
         const size_t i = base + threadIdx.x;
         Fr s = Fr::zero();
-        if (i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
+        if (threadIdx.x < stripe && i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
         DigitStream ds(s);
         for (int w = 0; w < windows; w++) {
             const uint32_t mag = ds.next(c) & 0x7fffffffu;
@@ -302,15 +303,16 @@ __global__ void __launch_bounds__(1024) msm_bin_scan_kernel(const uint32_t* __re
 
 __global__ void __launch_bounds__(kBinThreads) msm_bin_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ bin_offsets,
                                                                       uint32_t* __restrict__ bin_cursor, uint32_t* __restrict__ part,
-                                                                      size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins, int table) {
+                                                                      size_t n, int c, int windows, int groups, uint32_t nb, uint32_t nbins, int table,
+                                                                      uint32_t stripe) {
     __shared__ uint32_t s_cnt[kMaxBins];
     __shared__ uint32_t s_base[kMaxBins];
-    for (size_t base = (size_t)blockIdx.x * kBinThreads; base < n; base += (size_t)gridDim.x * kBinThreads) {
+    for (size_t base = (size_t)blockIdx.x * stripe; base < n; base += (size_t)gridDim.x * stripe) {
         for (uint32_t b = threadIdx.x; b < nbins; b += kBinThreads) s_cnt[b] = 0;
         __syncthreads();
         const size_t i = base + threadIdx.x;
         Fr s = Fr::zero();
-        if (i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
+        if (threadIdx.x < stripe && i < n) s = Fr::load_nc(scalars + 2 * i).from_mont();
         // one counting round: the rank of every entry inside its (stripe, bin) stays in registers, two 16-bit ranks per
         // word (a stripe has at most 1024 * 32 entries)
         uint32_t rk[kMaxWindows / 2];
@@ -972,12 +974,19 @@ static int msm_enqueue(zkw_ctx* ctx, int lane, int which_bases, const uint64_t* 
         uint32_t* bin_offsets = (uint32_t*)(ws + o_bin_offsets);
         uint32_t* chunk_first = (uint32_t*)(ws + o_chunk_first);
         uint32_t* chunk_base = (uint32_t*)(ws + o_chunk_base);
-        const unsigned stripes = (unsigned)std::min<size_t>((n + kBinThreads - 1) / kBinThreads, 2 * (size_t)ctx->sm_count);
-        { ProfScope ps_(ctx, "msm_bin_count_kernel", st); msm_bin_count_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_counts, n, c, p.windows, p.groups, p.nb, nbins); }
+        // One CTA of 1024 threads is resident per SM (48 registers), so the scalars are cut into stripes such that every SM
+        // gets the same number of them: 2^19 scalars over 148 SMs = 3.46 full stripes, i.e. four rounds with a quarter of the
+        // SMs idle in the last; 592 stripes of 896 scalars are four full rounds.
+        const size_t sms = (size_t)ctx->sm_count;
+        const size_t rounds = (n + sms * kBinThreads - 1) / (sms * kBinThreads);
+        uint32_t stripe = (uint32_t)((n + sms * rounds - 1) / (sms * rounds));
+        stripe = std::min<uint32_t>(kBinThreads, (stripe + 31u) & ~31u);
+        const unsigned stripes = (unsigned)std::min<size_t>((n + stripe - 1) / stripe, sms);
+        { ProfScope ps_(ctx, "msm_bin_count_kernel", st); msm_bin_count_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_counts, n, c, p.windows, p.groups, p.nb, nbins, stripe); }
         ZKW_LAUNCHED(ctx);
         { ProfScope ps_(ctx, "msm_bin_scan_kernel", st); msm_bin_scan_kernel<<<1, 1024, 0, st>>>(bin_counts, bin_offsets, chunk_first, nbins); }
         ZKW_LAUNCHED(ctx);
-        { ProfScope ps_(ctx, "msm_bin_scatter_kernel", st); msm_bin_scatter_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_offsets, bin_cursor, digits, n, c, p.windows, p.groups, p.nb, nbins, table ? 1 : 0); }
+        { ProfScope ps_(ctx, "msm_bin_scatter_kernel", st); msm_bin_scatter_kernel<<<stripes, kBinThreads, 0, st>>>((const uint4*)scalars_dev, bin_offsets, bin_cursor, digits, n, c, p.windows, p.groups, p.nb, nbins, table ? 1 : 0, stripe); }
         ZKW_LAUNCHED(ctx);
         { ProfScope ps_(ctx, "msm_fine_count_kernel", st); msm_fine_count_kernel<<<(unsigned)max_chunks, kChunkThreads, 0, st>>>(digits, bin_offsets, bin_counts, chunk_first, nbins, counts, chunk_base); }
         ZKW_LAUNCHED(ctx);
