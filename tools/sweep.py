@@ -65,7 +65,8 @@ def main():
         row["msm_alg_gbs"] = 96 * n / ms / 1e6
         row["msm_frac_of_hbm"] = row["msm_alg_gbs"] / peak
         row["msm_points_per_s"] = n / ms * 1e3
-        row["msm_modmul_per_s"] = 16 * n * 10 / ms * 1e3    # 16 windows x (8M + 2S) per mixed addition
+        row["msm_windows"] = -(-255 // ctx.msm_window_bits(n))     # mixed additions per point: the plan the library picks for n
+        row["msm_modmul_per_s"] = row["msm_windows"] * n * 10 / ms * 1e3    # windows x (8M + 2S) per mixed addition, whole MSM time
         if k >= 17:
             a = rand_fr(n, gen, dev)
             ms = timed(stream, lambda: ctx.lagrange_to_coeff_dev(a, k), reps)
