@@ -811,6 +811,8 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
         ZKW_TRY(sc.get(u * 4, (void**)&rank)); ZKW_TRY(sc.get((m + 1) * 4, (void**)&counts));
         ZKW_TRY(sc.get((m + 1) * 4, (void**)&run_start)); ZKW_TRY(sc.get((m + 1) * 4, (void**)&rep_start));
         ZKW_TRY(sc.get((m + 1) * 4, (void**)&desc_start)); ZKW_TRY(sc.get(4, (void**)&err));
+        uint32_t* tile_tot;
+        ZKW_TRY(sc.get(3 * std::max<size_t>(1, ((size_t)m + kLookupTile - 1) / kLookupTile) * 4, (void**)&tile_tot));
         ZKW_CUDA(ctx, cudaMemsetAsync(err, 0, 4, st));
         for (unsigned l = 0; l < nlk; l++) {
             if (L) lk_inp[l] = adv[A + l];
@@ -823,7 +825,12 @@ static int create_proof_impl(zkw_ctx* ctx, const zkw_pk* pk, const uint64_t* con
             ZKW_CUDA(ctx, cudaMemsetAsync(counts, 0, (m + 1) * 4, st));
             { ProfScope ps_(ctx, "lookup_rank_kernel"); lookup_rank_kernel<<<grid_for(u, 128), 128, 0, st>>>((const uint4*)lk_inp[l], (const uint4*)pk->table_canon, m, rank, counts, err, u, lookup_probe); }
             ZKW_LAUNCHED(ctx);
-            { ProfScope ps_(ctx, "lookup_scan_kernel"); lookup_scan_kernel<<<1, 1024, 0, st>>>(counts, pk->table_mult, m, run_start, rep_start, desc_start, err); }
+            {
+                const unsigned tiles = std::max(1u, (m + kLookupTile - 1) / kLookupTile);
+                { ProfScope ps_(ctx, "lookup_scan_totals_kernel"); lookup_scan_totals_kernel<<<tiles, 1024, 0, st>>>(counts, pk->table_mult, m, tile_tot, err); }
+                ZKW_LAUNCHED(ctx);
+                { ProfScope ps_(ctx, "lookup_scan_kernel"); lookup_scan_kernel<<<tiles, 1024, 0, st>>>(counts, pk->table_mult, m, tile_tot, run_start, rep_start, desc_start, err); }
+            }
             ZKW_LAUNCHED(ctx);
             uint32_t herr = 0;
             ZKW_CUDA(ctx, cudaMemcpyAsync(&herr, err, 4, cudaMemcpyDeviceToHost, st));

@@ -272,28 +272,39 @@ __device__ __forceinline__ int cmp256(const Fr& a, const Fr& b) {
 __global__ void lookup_rank_kernel(const uint4* inp, const uint4* table_sorted_canon, uint32_t m, uint32_t* rank, uint32_t* counts,
                                    uint32_t* error_flag, size_t u, int probe) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= u) return;
-    const Fr v = Fr::load(inp + 2 * i).from_mont();
-    uint32_t lo = 0, hi = m;  // first index with table[idx] >= v
-    // range tables hold 0 .. T-1 in order, so a value below m is (almost always) its own rank: one probe instead of log2(m)
-    // dependent loads; anything else takes the binary search
-    if (probe && !(v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) && v.l[0] < m &&
-        cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)v.l[0]), v) == 0) {
-        rank[i] = v.l[0];
-        atomicAdd(&counts[v.l[0]], 1u);
-        return;
+    // every lane stays to the end: the histogram add is aggregated per warp (below)
+    uint32_t found = 0xffffffffu;   // rank of this row's value, or none
+    if (i < u) {
+        const Fr v = Fr::load(inp + 2 * i).from_mont();
+        // range tables hold 0 .. T-1 in order, so a value below m is (almost always) its own rank: one probe instead of log2(m)
+        // dependent loads; anything else takes the binary search
+        if (probe && !(v.l[1] | v.l[2] | v.l[3] | v.l[4] | v.l[5] | v.l[6] | v.l[7]) && v.l[0] < m &&
+            cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)v.l[0]), v) == 0) {
+            found = v.l[0];
+        } else {
+            uint32_t lo = 0, hi = m;  // first index with table[idx] >= v
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)mid), v) < 0) lo = mid + 1; else hi = mid;
+            }
+            if (lo >= m || cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)lo), v) != 0) {
+                atomicExch(error_flag, 1u);  // ConstraintSystemFailure upstream: lookup input not in table
+                rank[i] = 0;
+            } else {
+                found = lo;
+            }
+        }
+        if (found != 0xffffffffu) rank[i] = found;
     }
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)mid), v) < 0) lo = mid + 1; else hi = mid;
+    // The lookup input of the ECDSA circuit is q_lookup * advice: seven rows of eight hold 0, so one address took 460 000 of the
+    // 2^19 atomic adds and L2 serialised them (0.32 ms for a kernel whose loads take 10 us).  Lanes that agree on the rank
+    // find each other (match.any) and the lowest one adds for the group.
+    __syncwarp();
+    const unsigned have = __ballot_sync(0xffffffffu, found != 0xffffffffu);
+    if (found != 0xffffffffu) {
+        const unsigned peers = __match_any_sync(have, found);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&counts[found], (uint32_t)__popc(peers));
     }
-    if (lo >= m || cmp256(Fr::load_nc(table_sorted_canon + 2 * (size_t)lo), v) != 0) {
-        atomicExch(error_flag, 1u);  // ConstraintSystemFailure upstream: lookup input not in table
-        rank[i] = 0;
-        return;
-    }
-    rank[i] = lo;
-    atomicAdd(&counts[lo], 1u);
 }
 
 // three exclusive scans over the m distinct table values in one single-CTA kernel:
@@ -310,61 +321,103 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, int lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m, uint32_t* run_start,
-                                                           uint32_t* rep_start, uint32_t* desc_start, uint32_t* error_flag) {
-    // four consecutive entries per thread and tile (4096 per tile): a quarter of the barrier-separated iterations of the
-    // one-entry-per-thread form - this kernel sits alone on the proof's critical path between the lookup ranks and A' / S'
+// Two launches over tiles of 4096 entries (four consecutive entries per thread, one CTA per tile): the tile totals, then every
+// CTA sums the totals of the tiles before it and scans its own tile.  (One CTA walking all 64 tiles of a 2^18-entry table with
+// barriers in between took 0.32 ms on the proof's critical path between the lookup ranks and A' / S'.)
+constexpr uint32_t kLookupTile = 4096;
+__device__ __forceinline__ void lookup_scan_entry(const uint32_t* counts, const uint32_t* mult, uint32_t m, uint32_t j, uint32_t q[3],
+                                                  uint32_t* error_flag) {
+    const uint32_t cj = counts[j];
+    q[0] = cj;
+    q[1] = cj ? cj - 1 : 0;
+    const uint32_t jj = m - 1 - j;
+    const uint32_t cjj = counts[jj], mu = mult[jj];
+    if (cjj && mu == 0) atomicExch(error_flag, 1u);
+    q[2] = mu - (cjj ? 1u : 0u);
+}
+
+__global__ void __launch_bounds__(1024) lookup_scan_totals_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m,
+                                                                  uint32_t* tile_tot /* [3][tiles] */, uint32_t* error_flag) {
+    __shared__ uint32_t wsum[3][32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t tot[3] = {0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t j = blockIdx.x * kLookupTile + 4 * (uint32_t)t + e;
+        if (j < m) {
+            uint32_t q[3];
+            lookup_scan_entry(counts, mult, m, j, q, error_flag);
+            tot[0] += q[0]; tot[1] += q[1]; tot[2] += q[2];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) tot[k] += __shfl_xor_sync(0xffffffffu, tot[k], d);
+        if (lane == 0) wsum[k][warp] = tot[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t v = wsum[k][lane];
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) tile_tot[(size_t)k * gridDim.x + blockIdx.x] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) lookup_scan_kernel(const uint32_t* counts, const uint32_t* mult, uint32_t m, const uint32_t* tile_tot,
+                                                           uint32_t* run_start, uint32_t* rep_start, uint32_t* desc_start, uint32_t* error_flag) {
     __shared__ uint32_t wsum[3][32];
     __shared__ uint32_t carry[3];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t < 3) carry[t] = 0;
+    const uint32_t tiles = gridDim.x;
+    if (warp < 3) {   // warp k: total of the tiles before this one, array k
+        uint32_t v = 0;
+        for (uint32_t b = lane; b < blockIdx.x; b += 32) v += tile_tot[(size_t)warp * tiles + b];
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) carry[warp] = v;
+    }
+    uint32_t q[3][4];
+    uint32_t tot[3] = {0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const uint32_t j = blockIdx.x * kLookupTile + 4 * (uint32_t)t + e;
+        q[0][e] = q[1][e] = q[2][e] = 0;
+        if (j < m) {
+            uint32_t qq[3];
+            lookup_scan_entry(counts, mult, m, j, qq, error_flag);
+            q[0][e] = qq[0]; q[1][e] = qq[1]; q[2][e] = qq[2];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) tot[k] += q[k][e];
+    }
+    uint32_t inc[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        inc[k] = warp_incl_scan_u32(tot[k], lane);
+        if (lane == 31) wsum[k][warp] = inc[k];
+    }
     __syncthreads();
-    for (uint32_t base = 0; base < m; base += 4096) {
-        uint32_t q[3][4];
-        uint32_t tot[3] = {0, 0, 0};
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) wsum[k][lane] = warp_incl_scan_u32(wsum[k][lane], lane);
+    }
+    __syncthreads();
+    uint32_t* outs[3] = {run_start, rep_start, desc_start};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        uint32_t run = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - tot[k];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
-            const uint32_t j = base + 4 * (uint32_t)t + e;
-            q[0][e] = q[1][e] = q[2][e] = 0;
-            if (j < m) {
-                const uint32_t cj = counts[j];
-                q[0][e] = cj;
-                q[1][e] = cj ? cj - 1 : 0;
-                const uint32_t jj = m - 1 - j;
-                const uint32_t cjj = counts[jj], mu = mult[jj];
-                if (cjj && mu == 0) atomicExch(error_flag, 1u);
-                q[2][e] = mu - (cjj ? 1u : 0u);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++) tot[k] += q[k][e];
+            const uint32_t j = blockIdx.x * kLookupTile + 4 * (uint32_t)t + e;
+            if (j < m) { outs[k][j] = run; run += q[k][e]; }
         }
-        uint32_t inc[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            inc[k] = warp_incl_scan_u32(tot[k], lane);
-            if (lane == 31) wsum[k][warp] = inc[k];
-        }
-        __syncthreads();
-        if (warp == 0) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) wsum[k][lane] = warp_incl_scan_u32(wsum[k][lane], lane);
-        }
-        __syncthreads();
-        uint32_t* outs[3] = {run_start, rep_start, desc_start};
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            uint32_t run = carry[k] + (warp ? wsum[k][warp - 1] : 0u) + inc[k] - tot[k];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const uint32_t j = base + 4 * (uint32_t)t + e;
-                if (j < m) { outs[k][j] = run; run += q[k][e]; }
-            }
-        }
-        __syncthreads();
-        if (t < 3) carry[t] += wsum[t][31];
-        __syncthreads();
+        if (blockIdx.x == tiles - 1 && t == 1023) outs[k][m] = carry[k] + wsum[k][31];   // grand totals
     }
-    if (t == 0) { run_start[m] = carry[0]; rep_start[m] = carry[1]; desc_start[m] = carry[2]; }
 }
 
 // last index q in [0, m) with start[q] <= x  (starts non-decreasing, start[m] = total > x)
