@@ -51,8 +51,10 @@ constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
 // second, nearly empty wave.  With W waves the runs are W times shorter and that tail is bounded by 1/W of the kernel.
 // Measured (tools/msm_ab.py, same call): W = 1 / 2 / 3 / 4 -> uniform MSM 1.955 / 1.93 / 1.92 / 1.93 ms, k = 19 proof
 // 27.38 / 27.47 / 27.46 / 27.75 ms: the proof is multiplier-bound either way, one wave keeps the partials fewest.
+// Re-measured with the final round-2 build (binned sort, c = 17; same call, twice): W = 1 / 2 / 3 -> MSM 1.602 / 1.585 / 1.608 ms,
+// proof 24.24 / 24.12 / 24.22 ms: two waves it is (the sort and combine kernels of the other lanes now find a slot mid-kernel).
 #ifndef ZKW_MSM_WAVES
-#define ZKW_MSM_WAVES 1
+#define ZKW_MSM_WAVES 2
 #endif
 constexpr int kAccThreads = 128;
 #ifndef ZKW_MSM_MIN_RUN
