@@ -56,7 +56,10 @@ constexpr int kAccSmemReserve = ZKW_MSM_SMEM_RESERVE;
 #ifndef ZKW_MSM_WAVES
 #define ZKW_MSM_WAVES 2
 #endif
-constexpr int kAccThreads = 128;
+#ifndef ZKW_MSM_ACC_THREADS
+#define ZKW_MSM_ACC_THREADS 128
+#endif
+constexpr int kAccThreads = ZKW_MSM_ACC_THREADS;
 #ifndef ZKW_MSM_MIN_RUN
 #define ZKW_MSM_MIN_RUN 16
 #endif
