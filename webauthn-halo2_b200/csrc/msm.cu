@@ -793,9 +793,15 @@ static int pick_window_bits(const zkw_ctx* ctx, size_t n) {
     //   2^19: c=16 2.02, c=17 2.01 (a tie; 16 keeps the tables' 16 windows)
     // With the binned entry sort and the cheaper bucket combine (round 2) the 2^19 tie went to c = 17: 15 windows instead of
     // 16 (-6 % additions) against twice the buckets: MSM 1.709 -> 1.634 ms, k = 19 proof 25.23 -> 24.71 ms (c = 19: 1.865 / 26.12).
+    // Below 2^17 points the bucket reduction's dependent chain is a third of the MSM and fewer buckets win: c = 15 (17 windows,
+    // 2^14 buckets) against 16 - 2^16 points 0.458 / 0.509 ms, 2^15 points 0.339 / 0.365 ms; at 2^17 points 0.672 / 0.653 ms alone
+    // (the k = 17 proof, resident: 11.13 against 11.40 ms in one run, its end-to-end time unchanged) - 16 stays there.  (Narrower
+    // windows put more than kLight partials into EVERY bucket - the run length cannot go below kMinRun - and the whole bucket
+    // set lands in the warp-per-bucket queue: c = 14 at 2^17: 1.12 ms.)
     if (n >= (1u << 22)) return 20;
     if (n >= (1u << 19)) return 17;
-    return n >= (1u << 13) ? 16 : 8;
+    if (n >= (1u << 17)) return 16;
+    return n >= (1u << 13) ? 15 : 8;
 }
 
 int msm_window_bits(const zkw_ctx* ctx, size_t n) { return pick_window_bits(ctx, n); }
