@@ -11,18 +11,20 @@
 //              window w, so all windows share ONE set of 2^(c-1) buckets and there is no per-window
 //              doubling chain at the end ("groups" G = 1).  Caller-supplied bases use one bucket set
 //              per window (G = W) and the windows are combined on the host.
-//   sort       counting sort of the (window, point) entries by bucket: histogram (atomics in L2),
-//              single-CTA scan, scatter.
-//   accumulate the sorted entry list is cut into EQUAL runs of L = ceil(E / T) entries, T = one resident
-//              wave of threads (CTAs per SM x SMs x 128), so the grid is exactly one wave and every thread
-//              does the same number of mixed XYZZ additions (8M + 2S each) whatever the scalar distribution
-//              (witness columns are far from uniform: zeros, bits, small limbs) - no partial last wave.
+//   sort       counting sort of the (window, point) entries by bucket.  Default: binned - coarse bins of 128 buckets, every
+//              count and rank taken in shared memory, chunks of a bin staged by one TMA bulk copy (bin_count, bin_scan,
+//              bin_scatter, fine_count, scan, fine_scatter; see "binned counting sort" below).  Small, very large or
+//              oddly shaped MSMs: direct - histogram (atomics in L2), single-CTA scan, scatter.
+//   accumulate the sorted entry list is cut into EQUAL runs of L = ceil(E / T) entries, T = ZKW_MSM_WAVES resident waves of
+//              threads (CTAs per SM x SMs x 128 each), so every thread does the same number of mixed XYZZ additions (8M + 2S
+//              each) whatever the scalar distribution (witness columns are far from uniform: zeros, bits, small limbs).
 //              A run crosses bucket boundaries: thread t emits its sum for bucket b to partial slot t + b
 //              (strictly increasing along the entry list, so a bucket's partials are contiguous and their
 //              range follows from the bucket's offsets alone).  The next affine point is prefetched (two
 //              128-bit loads per coordinate) while the current one is added.
-//   combine    one thread per bucket folds its (typically 3-4) partials; buckets cut into more than
-//              kLight runs (skewed scalars) are queued and get one CTA each: strided loop + shuffle tree.
+//   combine    one thread per bucket folds its (typically 2-4) partials; buckets cut into more than kLight runs (skewed
+//              scalars) are queued: up to kMedium partials one warp each, above that one CTA, the heaviest split over
+//              several CTAs whose sums the last one to finish folds.
 //   reduce     sum_b b * B_b by rows and columns of the bucket index (b - 1 = hi * 2^lb + lo): tree sums of
 //              every row and column, then two short bit-sliced weighted sums; the final ~2c-step Horner
 //              runs on the host in microseconds instead of as a latency-bound chain on the device.
