@@ -15,6 +15,8 @@ rows and 14 cosets, 1 iNTT(2^21), plus lookup permutation, grand products, evalu
                 hot-path call sequence through the three host-pointer seams a [patch]ed halo2_proofs would bind
     batch       BASELINE configs[2]/[3]: 64 proofs per GPU through zkw_prove_batch with three provers in flight
     split_msm   (N > 1) BASELINE configs[4]'s multi-GPU leg: one 2^20 / 2^22-point MSM split over the ranks
+    sweep       (N = 1) BASELINE configs[4]'s single-GPU leg: MSM 2^16 .. 2^24 points and iNTT / coset extension 2^17 .. 2^24,
+                milliseconds and fraction of the HBM roofline by algorithmic bytes (tools/sweep.py's code; --no-sweep skips it)
     roofline    the dominant kernel (msm_accumulate_kernel): algorithmic bytes / measured launch time against the measured
                 HBM copy bandwidth; DRAM traffic and the ALU ceiling are read from the committed ncu export / profiles
     cpu_baseline / --impl reference
@@ -29,6 +31,7 @@ from __future__ import annotations
 
 import argparse
 import importlib
+import importlib.util
 import json
 import os
 import subprocess
@@ -672,6 +675,24 @@ def run_b200(args):
     if world > 1 and args.split_msm and args.workload != "hotpath":
         split = split_msm_leg(zkw, torch, dist, rank, world, local)
 
+    # BASELINE configs[4], single-GPU leg (N = 1 only): the MSM sweep 2^16 .. 2^24 and the NTT sweep 2^17 .. 2^24 against the
+    # algorithmic-byte roofline, so that the driver's bench record carries them (tools/sweep.py is the same code, stand-alone)
+    sweep = None
+    if world == 1 and args.sweep and args.workload != "hotpath":
+        spec = importlib.util.spec_from_file_location("zkw_sweep", os.path.join(ROOT, "tools", "sweep.py"))
+        sw = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(sw)
+        hbm_peak = peaks()[0]["hbm_gbs"]
+        rows = sw.sweep_rows(zkw, 16, args.sweep_max_k, hbm_peak, local)
+        torch.cuda.set_stream(stream)
+        sweep = {"hbm_peak_gbs": hbm_peak,
+                 "algorithmic_bytes": "MSM 96*N, NTT 64*N, coset extension 160*n (SURVEY.md 8d)",
+                 "msm_ms": {str(r["k"]): round(r["msm_ms"], 4) for r in rows},
+                 "msm_frac_of_hbm": {str(r["k"]): round(r["msm_frac_of_hbm"], 5) for r in rows},
+                 "intt_ms": {str(r["k"]): round(r["intt_ms"], 4) for r in rows if "intt_ms" in r},
+                 "intt_frac_of_hbm": {str(r["k"]): round(r["intt_frac_of_hbm"], 5) for r in rows if "intt_frac_of_hbm" in r},
+                 "coset_ext_ms": {str(r["k"]): round(r["coset_ext_ms"], 4) for r in rows if "coset_ext_ms" in r}}
+
     if rank == 0:
         pk, pk_src = peaks()
         n = 1 << args.k
@@ -717,7 +738,7 @@ def run_b200(args):
             "circuit": state.state.circuit.stats() if args.workload != "hotpath" else None,
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample},
-            "e2e": e2e, "batch": batch, "split_msm": split, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
+            "e2e": e2e, "batch": batch, "split_msm": split, "sweep": sweep, "flavours": flavours, "gpu_launches": launches, "clocks": clocks, "kernels": kernels,
             "published_reference": {"value": 1.0 / 14.846241542, "unit": UNIT, "hardware": "M1 Pro (halo2-circuits/src/results/ecdsa_bench.csv:2)",
                                     "note": "full create_proof incl. halo2-ecc witness synthesis, Blake2b + SHPLONK; not the same hardware or witness"},
         }
@@ -742,6 +763,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-split-msm", dest="split_msm", action="store_false", help="N > 1: skip the single-MSM-split-over-ranks leg")
     ap.add_argument("--no-three-seam", dest="three_seam", action="store_false", help="skip the host-pointer three-seam figure")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="N = 1: skip the MSM / NTT size sweep (BASELINE configs[4])")
+    ap.add_argument("--sweep-max-k", type=int, default=24)
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the
     # first collective), so file descriptor 1 is pointed at stderr for the whole run and the JSON line alone goes

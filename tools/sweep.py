@@ -38,29 +38,24 @@ def rand_fr(n, gen, dev):
     return t
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--min-k", type=int, default=16)
-    ap.add_argument("--max-k", type=int, default=24)
-    ap.add_argument("--out", default="")
-    args = ap.parse_args()
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
-    dev = torch.device("cuda", 0)
+def sweep_rows(zkw_mod, min_k, max_k, peak, device=0, log=None):
+    """One row per size: MSM over the resident window tables, inverse / forward transform, coset extension (k >= 17)."""
+    dev = torch.device("cuda", device)
     gen = torch.Generator(device=dev)
     gen.manual_seed(7)
     tau = np.array([0x1234567890ABCDEF, 0x0FEDCBA987654321, 0x1111111111111111, 0x0222222222222222], dtype=np.uint64)
     rows = []
-    for k in range(args.min_k, args.max_k + 1):
+    for k in range(min_k, max_k + 1):
         n = 1 << k
-        ctx = zkw.Context(0)
-        stream = torch.cuda.ExternalStream(ctx.stream, device=0)
+        ctx = zkw_mod.Context(device)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=device)
         torch.cuda.set_stream(stream)
         row = {"k": k, "n": n}
         reps = 5 if k <= 21 else 3
         ctx.srs_setup(k, tau)
         s = rand_fr(n, gen, dev)
         torch.cuda.synchronize()
-        ms = timed(stream, lambda: ctx.msm_dev(s, n, zkw.BASES_G), reps)
+        ms = timed(stream, lambda: ctx.msm_dev(s, n, zkw_mod.BASES_G), reps)
         row["msm_ms"] = ms
         row["msm_alg_gbs"] = 96 * n / ms / 1e6
         row["msm_frac_of_hbm"] = row["msm_alg_gbs"] / peak
@@ -83,11 +78,24 @@ def main():
                 row["coset_ext_ms"] = ms
                 row["coset_ext_alg_gbs"] = 160 * n / ms / 1e6
                 del e
+            del a
         rows.append(row)
-        print(json.dumps(row), file=sys.stderr, flush=True)
+        if log:
+            print(json.dumps(row), file=log, flush=True)
         ctx.close()
         del s
         torch.cuda.empty_cache()
+    return rows
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--min-k", type=int, default=16)
+    ap.add_argument("--max-k", type=int, default=24)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    rows = sweep_rows(zkw, args.min_k, args.max_k, peak, 0, sys.stderr)
     doc = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak, "modmul_peak_per_s": 68.5e9, "rows": rows}
     text = json.dumps(doc, indent=1)
     if args.out:
