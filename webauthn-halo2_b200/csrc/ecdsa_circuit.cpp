@@ -326,7 +326,7 @@ struct Structure {   // what keygen needs; filled by the structure pass
     std::vector<Checkpoint> checkpoints;
 };
 
-struct Builder {
+struct alignas(64) Builder {   // cache-line aligned: the synthesis workers hold adjacent copies (no false sharing between them)
     // parameters
     unsigned k, A, L, F, lb, LB;
     uint64_t n, u;
@@ -1574,6 +1574,9 @@ extern "C" int zkw_ecdsa_synthesize(const zkw_ecdsa_circuit* c, const uint8_t pu
         std::vector<Builder> workers(nthreads, b);        // copies: own cursor, shared output columns and pre-pass results
         std::vector<char> done_ok(nthreads, 0);
         std::atomic<unsigned> next_chunk{0};
+        // every worker bumps rows[column] at the end of each region; the copies' tiny heap arrays would sit side by side in
+        // one cache line (false sharing), so each gets a line of its own
+        for (auto& w : workers) w.rows.reserve(32);
         auto body = [&](unsigned t) {
             Builder& w = workers[t];
             timespec ts0, ts1;
