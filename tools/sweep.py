@@ -96,7 +96,16 @@ def main():
     args = ap.parse_args()
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     rows = sweep_rows(zkw, args.min_k, args.max_k, peak, 0, sys.stderr)
-    doc = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak, "modmul_peak_per_s": 68.5e9, "rows": rows}
+    # measured 254-bit Montgomery products per second (tools/modmul_bench.cu), from the newest committed record
+    import glob
+    import re
+    modmul_peak, modmul_src = None, None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_modmul_peak.txt")), reverse=True):
+        vals = [float(x) for x in re.findall(r"([0-9.]+)\s*G\s*(?:products|modmul)", open(path).read())]
+        if vals:
+            modmul_peak, modmul_src = max(vals) * 1e9, os.path.relpath(path, ROOT)
+            break
+    doc = {"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": peak, "modmul_peak_per_s": modmul_peak, "modmul_peak_source": modmul_src, "rows": rows}
     text = json.dumps(doc, indent=1)
     if args.out:
         with open(args.out, "w") as f:
